@@ -1,0 +1,398 @@
+"""TEST INFRASTRUCTURE — stand-in `jax` / `warp` modules so the REFERENCE's own Python can run here.
+
+The reference (Autodesk/XLB, /root/reference) is 100 % Python but imports `jax` and `warp` at module import time;
+neither is installed or installable in the build container (no network, no wheel).  All LBM arithmetic of the
+reference's JAX backend is written out in the reference's own files as array expressions (`jnp.roll`, `jnp.where`,
+`jnp.tensordot`, `x.at[i].set(v)` ...).  This package provides *only those array primitives*, backed by numpy and
+following JAX's dtype rules (float32 default, python scalars are weakly typed, int (+) float32 -> float32), plus inert
+placeholders for everything Warp-related (the Warp kernels are never executed — they need the real Warp compiler).
+
+`install()` puts the stand-ins into `sys.modules`; afterwards `import xlb` (with /root/reference on sys.path) works and
+`ComputeBackend.JAX` operators execute the reference's code line by line.  Used exclusively by
+tests/golden/make_golden.py to generate golden vectors (committed as .npz) and by tests that are skipped when
+/root/reference is absent.  Nothing in the product path imports this.
+"""
+
+from __future__ import annotations
+
+import sys
+import types
+
+import numpy as np
+
+_X64 = {"enabled": False}
+
+
+def _default_float():
+    return np.float64 if _X64["enabled"] else np.float32
+
+
+# ------------------------------------------------------------------------------------------------
+# array type with `.at[idx].set(value)` and JAX-like type promotion
+# ------------------------------------------------------------------------------------------------
+
+
+class _At:
+    def __init__(self, arr):
+        self._arr = arr
+
+    def __getitem__(self, idx):
+        return _AtIdx(self._arr, idx)
+
+
+class _AtIdx:
+    def __init__(self, arr, idx):
+        self._arr, self._idx = arr, idx
+
+    def set(self, value):
+        out = np.array(self._arr, copy=True).view(JArray)
+        out[self._idx] = np.asarray(value)
+        return out
+
+
+def _float_rank(dt):
+    return {np.dtype(np.float16): 1, np.dtype(np.float32): 2, np.dtype(np.float64): 3}.get(np.dtype(dt), 0)
+
+
+def _promote_inputs(inputs):
+    """JAX rule used by the reference's expressions: integer/bool arrays combined with a floating array take the
+    floating dtype (numpy would go to float64); numpy float64 *scalars* are treated as weak python floats."""
+    target, rank = None, 0
+    for x in inputs:
+        if isinstance(x, np.ndarray) and x.ndim > 0 and _float_rank(x.dtype) > rank:
+            target, rank = x.dtype, _float_rank(x.dtype)
+    if target is None:
+        return inputs
+    out = []
+    for x in inputs:
+        if isinstance(x, np.ndarray) and x.ndim > 0 and x.dtype.kind in "iu":
+            x = x.astype(target)
+        elif isinstance(x, (np.floating,)) or (isinstance(x, np.ndarray) and x.ndim == 0 and x.dtype.kind == "f"):
+            x = float(x) if _float_rank(getattr(x, "dtype", np.float64)) > rank else x
+        out.append(x)
+    return tuple(out)
+
+
+def _finish(x):
+    if isinstance(x, np.ndarray):
+        if x.dtype == np.float64 and not _X64["enabled"]:
+            x = x.astype(np.float32)
+        return x.view(JArray)
+    if isinstance(x, tuple):
+        return tuple(_finish(v) for v in x)
+    if isinstance(x, list):
+        return [_finish(v) for v in x]
+    return x
+
+
+class JArray(np.ndarray):
+    @property
+    def at(self):
+        return _At(self)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
+        raw = tuple(np.asarray(x) if isinstance(x, JArray) else x for x in inputs)
+        raw = _promote_inputs(raw)
+        if out is not None:
+            kwargs["out"] = tuple(np.asarray(o) if isinstance(o, JArray) else o for o in out)
+        res = getattr(ufunc, method)(*raw, **kwargs)
+        return _finish(res)
+
+    def astype(self, dtype, *a, **k):
+        return np.asarray(self).astype(dtype, *a, **k).view(JArray)
+
+    def block_until_ready(self):
+        return self
+
+
+# ------------------------------------------------------------------------------------------------
+# jax.numpy
+# ------------------------------------------------------------------------------------------------
+
+
+def _unwrap(x):
+    if isinstance(x, JArray):
+        return np.asarray(x)
+    if isinstance(x, (tuple, list)):
+        return type(x)(_unwrap(v) for v in x)
+    return x
+
+
+def _wrap_fn(name):
+    fn = getattr(np, name)
+
+    def wrapped(*args, **kwargs):
+        args = _promote_inputs(tuple(_unwrap(a) for a in args))
+        kwargs = {k: _unwrap(v) for k, v in kwargs.items()}
+        return _finish(fn(*args, **kwargs))
+
+    wrapped.__name__ = name
+    return wrapped
+
+
+def _jnp_array(obj, dtype=None, copy=True):
+    a = np.array(_unwrap(obj), dtype=dtype, copy=True)
+    if dtype is None:
+        if a.dtype == np.float64 and not _X64["enabled"]:
+            a = a.astype(np.float32)
+        elif a.dtype == np.int64 and not _X64["enabled"]:
+            a = a.astype(np.int32)
+    return a.view(JArray)
+
+
+def _creation(name):
+    fn = getattr(np, name)
+
+    def wrapped(shape, *args, dtype=None, **kwargs):
+        if dtype is None and name in ("zeros", "ones", "empty"):
+            dtype = _default_float()
+        return fn(shape, *args, dtype=dtype, **kwargs).view(JArray)
+
+    return wrapped
+
+
+def _jnp_full(shape, fill_value, dtype=None):
+    if dtype is None:
+        dtype = _default_float() if isinstance(fill_value, float) else None
+    return np.full(shape, fill_value, dtype=dtype).view(JArray)
+
+
+def _jnp_sqrt(x):
+    if isinstance(x, (int, float)):
+        return _default_float()(np.sqrt(_default_float()(x)))  # jax: computed and typed in the default float type
+    return _finish(np.sqrt(_unwrap(x)))
+
+
+def _jnp_tensordot(a, b, axes=2):
+    a, b = _promote_inputs((_unwrap(a), _unwrap(b)))
+    return _finish(np.tensordot(a, b, axes=axes))
+
+
+def _jnp_where(cond, x=None, y=None):
+    if x is None:
+        return tuple(v.view(JArray) for v in np.where(_unwrap(cond)))
+    x, y = _unwrap(x), _unwrap(y)
+    xs = [v for v in (x, y) if isinstance(v, np.ndarray) and v.ndim > 0]
+    res = np.where(_unwrap(cond), x, y)
+    if xs and all(v.dtype == xs[0].dtype for v in xs):
+        res = res.astype(xs[0].dtype, copy=False)
+    return _finish(res)
+
+
+def _jnp_pad(array, pad_width, mode="constant", **kwargs):
+    return _finish(np.pad(_unwrap(array), pad_width, mode=mode, **kwargs))
+
+
+def _make_jnp():
+    m = types.ModuleType("jax.numpy")
+    m.ndarray = np.ndarray  # `isinstance(x, jnp.ndarray)` is true for our arrays
+    m.array = _jnp_array
+    m.asarray = lambda obj, dtype=None: _jnp_array(obj, dtype=dtype)
+    for name in ("zeros", "ones", "empty"):
+        setattr(m, name, _creation(name))
+    m.full = _jnp_full
+    m.sqrt = _jnp_sqrt
+    m.tensordot = _jnp_tensordot
+    m.where = _jnp_where
+    m.pad = _jnp_pad
+    for name in (
+        "zeros_like", "ones_like", "sum", "square", "roll", "logical_and", "logical_or", "logical_not", "broadcast_to",
+        "stack", "arange", "meshgrid", "maximum", "minimum", "abs", "sin", "cos", "rint", "dot", "concatenate",
+        "reshape", "transpose", "mean", "max", "min", "linspace", "expand_dims", "squeeze", "any", "all", "isnan",
+    ):  # fmt: skip
+        setattr(m, name, _wrap_fn(name))
+    for name in ("float16", "float32", "float64", "int32", "int64", "uint8", "bool_", "pi", "newaxis", "inf", "nan"):
+        setattr(m, name, getattr(np, name))
+    return m
+
+
+# ------------------------------------------------------------------------------------------------
+# jax, jax.lax, sharding placeholders
+# ------------------------------------------------------------------------------------------------
+
+
+def _jit(fun=None, **kwargs):
+    if fun is None:
+        return lambda f: f
+    return fun
+
+
+def _vmap(fun, in_axes=0, out_axes=0):
+    def mapped(*args):
+        n = len(args[0])
+        outs = [fun(*[a[i] for a in args]) for i in range(n)]
+        return _finish(np.stack([np.asarray(o) for o in outs], axis=out_axes))
+
+    return mapped
+
+
+def _broadcast_in_dim(operand, shape, broadcast_dimensions):
+    operand = np.asarray(operand)
+    view = [1] * len(shape)
+    for src, dst in enumerate(broadcast_dimensions):
+        view[dst] = operand.shape[src]
+    return np.broadcast_to(operand.reshape(view), shape).view(JArray)
+
+
+class _Device:
+    platform = "cpu"
+    id = 0
+
+    def __repr__(self):
+        return "CpuDevice(shim)"
+
+
+_DEVICE = _Device()
+
+
+class _Mesh:
+    def __init__(self, devices, axis_names=None):
+        self.devices, self.axis_names = devices, axis_names
+
+
+class _PartitionSpec(tuple):
+    def __new__(cls, *args):
+        return super().__new__(cls, args)
+
+
+class _NamedSharding:
+    def __init__(self, mesh, spec):
+        self.mesh, self.spec = mesh, spec
+
+    def addressable_devices_indices_map(self, shape):
+        return {_DEVICE: tuple(slice(None) for _ in shape)}
+
+
+class _Permissive(types.ModuleType):
+    """Module whose unknown attributes are inert callables/types (for never-executed Warp/plotting code)."""
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        obj = _Inert(f"{self.__name__}.{name}")
+        setattr(self, name, obj)
+        return obj
+
+
+class _Inert:
+    def __init__(self, name="inert"):
+        self._name = name
+
+    def __call__(self, *a, **k):
+        # decorator use (@wp.func / @wp.kernel): hand the function back untouched
+        if len(a) == 1 and not k and callable(a[0]) and not isinstance(a[0], _Inert):
+            return a[0]
+        return _Inert(self._name + "()")
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Inert(self._name + "." + name)
+
+    def __getitem__(self, k):
+        return self
+
+    def __mro_entries__(self, bases):
+        return (object,)
+
+    def __repr__(self):
+        return f"<inert {self._name}>"
+
+
+def _make_warp():
+    wp = _Permissive("warp")
+    wp.constant = lambda x: x
+    wp.init = lambda *a, **k: None
+    wp.synchronize = lambda *a, **k: None
+
+    def _vec(*a, **k):
+        return lambda *vals: np.asarray(vals[0]) if vals else None
+
+    wp.vec = _vec
+    wp.mat = _vec
+    for n, t in (("float16", np.float16), ("float32", np.float32), ("float64", np.float64), ("uint8", np.uint8), ("int32", np.int32), ("bool", np.bool_)):
+        setattr(wp, n, t)
+    wp.sqrt = lambda x: float(np.sqrt(x))
+    utils = _Permissive("warp.utils")
+    wp.utils = utils
+    return wp, utils
+
+
+_DUMMY_MODULES = (
+    "trimesh", "pyvista", "matplotlib", "matplotlib.pylab", "matplotlib.pyplot", "matplotlib.cm", "cupy", "stl", "PIL",
+    "PIL.Image", "pxr", "kvikio", "kvikio._lib", "kvikio._lib.arr", "mpi4py",
+)  # fmt: skip
+
+
+def install():
+    """Register the stand-ins in sys.modules (idempotent).  Refuses to shadow a real jax installation."""
+    if "jax" in sys.modules and not getattr(sys.modules["jax"], "__refshim__", False):
+        raise RuntimeError("a real `jax` is already imported; the stand-in must not shadow it")
+    if getattr(sys.modules.get("jax"), "__refshim__", False):
+        return
+    jax = types.ModuleType("jax")
+    jax.__refshim__ = True
+    jax.__path__ = []
+    jnp = _make_jnp()
+    lax = types.ModuleType("jax.lax")
+    lax.broadcast_in_dim = _broadcast_in_dim
+
+    def _no_ppermute(*a, **k):
+        raise NotImplementedError("ppermute needs real multi-device jax; the oracle emulates it (stream_sharded)")
+
+    lax.ppermute = _no_ppermute
+    sharding = types.ModuleType("jax.sharding")
+    sharding.PartitionSpec, sharding.NamedSharding, sharding.Mesh = _PartitionSpec, _NamedSharding, _Mesh
+    experimental = types.ModuleType("jax.experimental")
+    experimental.__path__ = []
+    mesh_utils = types.ModuleType("jax.experimental.mesh_utils")
+    mesh_utils.create_device_mesh = lambda shape, *a, **k: np.full(shape, _DEVICE, dtype=object)
+    shard_map = types.ModuleType("jax.experimental.shard_map")
+    shard_map.shard_map = lambda f, **k: f
+    experimental.mesh_utils, experimental.shard_map = mesh_utils, shard_map
+    image = _Permissive("jax.image")
+    dlpack = _Permissive("jax.dlpack")
+
+    class _Config:
+        @staticmethod
+        def update(key, value):
+            if key == "jax_enable_x64":
+                _X64["enabled"] = bool(value)
+
+    jax.config = _Config()
+    jax.jit, jax.vmap = _jit, _vmap
+    jax.numpy, jax.lax, jax.sharding, jax.experimental, jax.image, jax.dlpack = jnp, lax, sharding, experimental, image, dlpack
+    jax.Array = np.ndarray
+    jax.devices = lambda *a: [_DEVICE]
+    jax.device_count = lambda: 1
+    jax.default_backend = lambda: "cpu"
+    jax.device_put = lambda x, d=None: x
+    jax.make_array_from_single_device_arrays = lambda shape, sharding, arrays: arrays[0]
+    mods = {
+        "jax": jax, "jax.numpy": jnp, "jax.lax": lax, "jax.sharding": sharding, "jax.experimental": experimental,
+        "jax.experimental.mesh_utils": mesh_utils, "jax.experimental.shard_map": shard_map, "jax.image": image,
+        "jax.dlpack": dlpack,
+    }  # fmt: skip
+    wp, wp_utils = _make_warp()
+    mods["warp"], mods["warp.utils"] = wp, wp_utils
+    for name in _DUMMY_MODULES:
+        if name not in sys.modules:
+            mods[name] = _Permissive(name)
+            mods[name].__path__ = []
+    sys.modules.update(mods)
+
+
+def set_x64(enabled: bool):
+    _X64["enabled"] = bool(enabled)
+
+
+def import_reference(path="/root/reference"):
+    """install() + import the reference package `xlb` from `path`; returns the module."""
+    install()
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    import xlb  # noqa: the reference
+
+    if not xlb.__file__.startswith(path):
+        raise RuntimeError(f"`xlb` resolved to {xlb.__file__}, not the reference under {path}")
+    return xlb
