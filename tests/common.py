@@ -1,0 +1,157 @@
+"""Shared builders for the tests: the same case expressed (a) for the CPU oracle and (b) through the xlb_b200 operator
+API, either from a golden fixture (tests/golden/*.npz, produced by the reference itself) or from scratch."""
+
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STEP_CASES = [
+    "cavity_d3q19_bgk_fp32",
+    "cavity_d3q19_bgk_fp32fp16",
+    "cavity_d3q19_bgk_fp64fp32",
+    "cavity_d3q27_kbc_fp32",
+    "cavity_d2q9_bgk_fp32",
+    "cavity_d2q9_kbc_fp32",
+    "sphere_d3q27_kbc_fp32",
+    "sphere_d3q19_bgk_fp32",
+    "sphere_d3q19_bgk_zouhe_pressure_fp32",
+    "sphere_d3q27_bgk_regpressure_fp64",
+    "sphere_d3q19_bgk_donothing_fp32",
+    "periodic_d3q19_bgk_fp32",
+    "periodic_d3q27_kbc_fp32",
+]
+# relative tolerance (max |a-b| / max |b|) per store/compute policy; north-star: 1e-5 fp32, 1e-3 fp16 storage
+RTOL = {"FP32FP32": 1e-5, "FP64FP32": 1e-5, "FP64FP64": 1e-9, "FP32FP16": 1e-3, "FP64FP16": 1e-3}
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False) as z:
+        g = {k: z[k] for k in z.files}
+    for k in ("lattice", "policy", "collision"):
+        g[k] = str(g[k])
+    g["shape"] = tuple(int(s) for s in g["shape"])
+    g["steps"], g["omega"], g["n_bc"] = int(g["steps"]), float(g["omega"]), int(g["n_bc"])
+    g["bcs"] = []
+    for i in range(g["n_bc"]):
+        b = {k[len(f"bc{i}_") :]: g[k] for k in g if k.startswith(f"bc{i}_")}
+        b["kind"], b["id"] = str(b["kind"]), int(b["id"])
+        if "bc_type" in b:
+            b["bc_type"] = str(b["bc_type"])
+        g["bcs"].append(b)
+    return g
+
+
+def unpack_bits(bits, q):
+    return np.stack([(bits >> np.uint32(l)) & np.uint32(1) for l in range(q)]).astype(bool)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+# ---- oracle side ------------------------------------------------------------------------------------------------
+
+
+def oracle_bcs(g):
+    from oracle import lbm_numpy as O
+
+    out = []
+    for b in g["bcs"]:
+        kw = {}
+        if b["kind"] == "equilibrium":
+            kw = dict(rho=float(b["rho"]), u=tuple(float(v) for v in b["u"]))
+        if b["kind"] in ("zouhe", "regularized"):
+            kw = dict(bc_type=b["bc_type"], prescribed=b["prescribed"])
+        out.append(O.BC(b["kind"], b["id"], b["indices"], **kw))
+    return out
+
+
+def oracle_run(g, steps=None, flavor="jax"):
+    from oracle import lbm_numpy as O
+
+    lat = O.Lattice(g["lattice"])
+    bcs = oracle_bcs(g)
+    if bcs:
+        bc_mask, missing = O.build_masks(bcs, g["shape"], lat, flavor=flavor)
+    else:  # the stepper skips the masker when no BC carries indices (nse_stepper.py:115-116)
+        bc_mask = np.zeros((1,) + g["shape"], np.uint8)
+        missing = np.zeros((lat.q,) + g["shape"], bool)
+    f = O.run(g["f_init"].copy(), bc_mask, missing, bcs, g["omega"], lat, g["steps"] if steps is None else steps, policy=g["policy"], collision=g["collision"], flavor="jax")
+    return f, bc_mask, missing
+
+
+# ---- xlb_b200 side (reference-style script) ----------------------------------------------------------------------
+
+
+def native_case(g, backend="WARP", cells_per_thread=0):
+    """Build grid, BCs (same ids as the fixture) and stepper through the operator API; returns
+    (stepper, f_0, f_1, bc_mask, missing_mask)."""
+    import torch
+
+    import xlb_b200 as xlb
+    from xlb_b200.compute_backend import ComputeBackend
+    from xlb_b200.grid import grid_factory
+    from xlb_b200.operator.boundary_condition import (
+        DoNothingBC,
+        EquilibriumBC,
+        ExtrapolationOutflowBC,
+        FullwayBounceBackBC,
+        HalfwayBounceBackBC,
+        RegularizedBC,
+        ZouHeBC,
+    )
+    from xlb_b200.operator.stepper import IncompressibleNavierStokesStepper
+
+    be = ComputeBackend[backend]
+    pp = xlb.PrecisionPolicy[g["policy"]]
+    vs = getattr(xlb.velocity_set, g["lattice"])(precision_policy=pp, compute_backend=be)
+    xlb.init(velocity_set=vs, default_backend=be, default_precision_policy=pp)
+    grid = grid_factory(g["shape"])
+    bcs = []
+    for b in g["bcs"]:
+        idx = [list(map(int, row)) for row in b["indices"]]
+        kind = b["kind"]
+        if kind == "equilibrium":
+            bc = EquilibriumBC(rho=float(b["rho"]), u=tuple(float(v) for v in b["u"]), indices=idx)
+        elif kind == "fullway":
+            bc = FullwayBounceBackBC(indices=idx)
+        elif kind == "halfway":
+            bc = HalfwayBounceBackBC(indices=idx)
+        elif kind == "donothing":
+            bc = DoNothingBC(indices=idx)
+        elif kind == "outflow":
+            bc = ExtrapolationOutflowBC(indices=idx)
+        elif kind in ("zouhe", "regularized"):
+            cls = ZouHeBC if kind == "zouhe" else RegularizedBC
+            pv = b["prescribed"]
+            if b["bc_type"] == "pressure":
+                bc = cls("pressure", prescribed_value=float(pv), indices=idx)
+            elif be == ComputeBackend.JAX:
+                bc = cls("velocity", profile=(lambda pv=pv: pv), indices=idx)
+            else:  # Warp convention: per-cell callable returning the normal velocity magnitude (x-inlet: u_x)
+                bc = cls("velocity", profile=(lambda index, pv=pv: [pv[0][index[1], index[2]]]), indices=idx)
+        else:
+            raise ValueError(kind)
+        bc.id = b["id"]
+        bcs.append(bc)
+    stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=bcs, collision_type=g["collision"], cells_per_thread=cells_per_thread)
+    f_init = g["f_init"] if be == ComputeBackend.JAX or len(g["shape"]) == 3 else g["f_init"][..., None]
+
+    def initializer(grid, velocity_set, precision_policy, compute_backend):
+        return xlb.field.as_field(torch.as_tensor(np.ascontiguousarray(f_init)), device=grid.device)
+
+    f_0, f_1, bc_mask, missing_mask = stepper.prepare_fields(initializer=initializer)
+    return stepper, f_0, f_1, bc_mask, missing_mask
+
+
+def native_run(g, backend="WARP", steps=None, cells_per_thread=0):
+    stepper, f_0, f_1, bc_mask, missing_mask = native_case(g, backend, cells_per_thread)
+    for i in range(g["steps"] if steps is None else steps):
+        f_0, f_1 = stepper(f_0, f_1, bc_mask, missing_mask, g["omega"], i)
+        f_0, f_1 = f_1, f_0
+    f = f_0.numpy()
+    if f.ndim == 4 and len(g["shape"]) == 2:
+        f = f[..., 0]
+    return f, bc_mask.numpy(), missing_mask.numpy()

@@ -1,0 +1,89 @@
+"""Parity of the fused CUDA step (through the operator API -> C ABI) against (a) vectors produced by the reference's own
+Python and (b) the CPU oracle.  Masks bit-exact; populations within the north-star tolerances
+(1e-5 relative fp32, 1e-3 fp16 storage)."""
+
+import numpy as np
+import pytest
+
+from common import RTOL, STEP_CASES, load_golden, native_run, oracle_run, rel_err, unpack_bits
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("backend", ["WARP", "JAX"])
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_step_matches_reference_vectors(name, backend):
+    g = load_golden(name)
+    q = g["f_final"].shape[0]
+    f, bc_mask, missing = native_run(g, backend=backend)
+    if g["n_bc"]:
+        if backend == "JAX" and len(g["shape"]) == 2:
+            pass
+        assert np.array_equal(bc_mask.reshape(g["bc_mask"].shape), g["bc_mask"]), "bc_mask must be bit-exact"
+        assert np.array_equal(missing.reshape((q,) + g["shape"]), unpack_bits(g["missing_bits"], q)), "missing_mask must be bit-exact"
+    assert f.dtype == g["f_final"].dtype
+    assert np.isfinite(f.astype(np.float64)).all()
+    assert rel_err(f, g["f_final"]) <= RTOL[g["policy"]], f"{name}: rel err {rel_err(f, g['f_final']):.3e}"
+
+
+@pytest.mark.parametrize("v", [1, 2, 4, 8])
+@pytest.mark.parametrize("name", ["cavity_d3q19_bgk_fp32", "cavity_d3q19_bgk_fp32fp16", "sphere_d3q27_kbc_fp32", "sphere_d3q27_bgk_regpressure_fp64", "cavity_d2q9_kbc_fp32"])
+def test_every_cells_per_thread_variant(name, v):
+    """All vector widths of the kernel compute the same step (the library falls back when v does not divide nz)."""
+    g = load_golden(name)
+    f, _, _ = native_run(g, cells_per_thread=v)
+    assert rel_err(f, g["f_final"]) <= RTOL[g["policy"]]
+
+
+def test_cavity_1000_steps_against_oracle():
+    """C1-style run (examples/performance/mlups_3d.py set-up) for 1000 steps at a size the numpy oracle finishes in
+    seconds; tolerance = north-star 1e-5 relative on populations, rho and u."""
+    from oracle import lbm_numpy as O
+
+    g = load_golden("cavity_d3q19_bgk_fp32")
+    n = 32
+    lat = O.Lattice("D3Q19")
+    box, box_ne = O.bounding_box_indices((n,) * 3), O.bounding_box_indices((n,) * 3, remove_edges=True)
+    walls = np.unique(np.concatenate([box[k] for k in ("bottom", "left", "right", "front", "back")], axis=1), axis=-1)
+    g.update(shape=(n, n, n), steps=1000, omega=1.0, f_init=O.initialize_eq((n,) * 3, lat))
+    g["bcs"] = [dict(kind="equilibrium", id=1, indices=box_ne["top"], rho=1.0, u=np.array([0.02, 0, 0])), dict(kind="fullway", id=2, indices=walls)]
+    ref, bm, mm = oracle_run(g)
+    f, bc_mask, missing = native_run(g)
+    assert np.array_equal(bc_mask, bm) and np.array_equal(missing, mm)
+    assert rel_err(f, ref) <= 1e-5
+    rho_r, u_r = O.macroscopic(ref, lat)
+    rho_n, u_n = O.macroscopic(f, lat)
+    assert rel_err(rho_n, rho_r) <= 1e-5
+    assert np.abs(u_n - u_r).max() <= 1e-5 * max(np.abs(u_r).max(), 0.02)
+
+
+def test_solid_cells_255_are_skipped():
+    """bc_mask == 255 => the cell is neither read nor written (reference: nse_stepper.py:356-358)."""
+    import torch
+
+    g = load_golden("cavity_d3q19_bgk_fp32")
+    from common import native_case
+
+    stepper, f_0, f_1, bc_mask, missing_mask = native_case(g)
+    bc_mask[0, 5:9, 5:9, 4:12] = 255
+    f_1.fill_(7.0)
+    before = f_1.clone()
+    stepper(f_0, f_1, bc_mask, missing_mask, 1.0, 0)
+    solid = (bc_mask[0] == 255).unsqueeze(0).expand_as(f_1)
+    assert torch.equal(f_1[solid], before[solid])
+    assert not torch.equal(f_1[~solid], before[~solid])
+
+
+def test_stepper_errors_are_loud():
+    import torch
+
+    from common import native_case
+
+    g = load_golden("cavity_d3q19_bgk_fp32")
+    stepper, f_0, f_1, bc_mask, missing_mask = native_case(g)
+    with pytest.raises(Exception, match="no CPU fallback"):
+        stepper(f_0.cpu(), f_1, bc_mask, missing_mask, 1.0, 0)
+    with pytest.raises(Exception, match="different buffers"):
+        stepper(f_0, f_0, bc_mask, missing_mask, 1.0, 0)
+    with pytest.raises(Exception):
+        stepper(f_0.to(torch.float16), f_1, bc_mask, missing_mask, 1.0, 0)

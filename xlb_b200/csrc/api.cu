@@ -1,0 +1,157 @@
+// extern "C" entry points of the hot path: stepper handle + one fused step (include/xlb_b200.h).
+#include "halo.cuh"
+#include "step_kernel.cuh"
+
+struct xlbn_stepper {
+  int lattice, collision, compute_dtype, store_dtype, cells_per_thread;
+  bool needs_missing;
+  xlbn::BcEntry* table;  // device, 256 entries
+  int device;
+};
+
+using namespace xlbn;
+
+namespace xlbn {
+template <> int dispatch_step<D3Q19, XLBN_BGK>(const StepCall&);
+template <> int dispatch_step<D3Q27, XLBN_BGK>(const StepCall&);
+template <> int dispatch_step<D3Q27, XLBN_KBC>(const StepCall&);
+template <> int dispatch_step<D2Q9, XLBN_BGK>(const StepCall&);
+template <> int dispatch_step<D2Q9, XLBN_KBC>(const StepCall&);
+}  // namespace xlbn
+
+extern "C" {
+
+int xlbn_version(void) { return XLBN_VERSION; }
+
+const char* xlbn_last_error(void) { return error_buffer(); }
+
+int xlbn_lattice_tables(int lattice, int32_t* c, double* w, int32_t* opp) {
+  auto fill = [&](auto tag) {
+    using L = decltype(tag);
+    for (int l = 0; l < L::Q; ++l) {
+      if (c)
+        for (int a = 0; a < 3; ++a) c[a * L::Q + l] = a < L::D ? L::c(a, l) : 0;
+      if (w) w[l] = L::w(l);
+      if (opp) opp[l] = L::opp(l);
+    }
+    return (int)L::Q;
+  };
+  switch (lattice) {
+    case XLBN_D2Q9: return fill(D2Q9{});
+    case XLBN_D3Q19: return fill(D3Q19{});
+    case XLBN_D3Q27: return fill(D3Q27{});
+    default: return fail(XLBN_E_ARG, "unknown lattice %d", lattice);
+  }
+}
+
+int xlbn_stepper_create(const xlbn_stepper_desc* desc, xlbn_stepper** out) {
+  if (!desc || !out) return fail(XLBN_E_ARG, "stepper_create: NULL argument");
+  if (desc->lattice < XLBN_D2Q9 || desc->lattice > XLBN_D3Q27) return fail(XLBN_E_ARG, "stepper_create: unknown lattice %d", desc->lattice);
+  if (desc->collision != XLBN_BGK && desc->collision != XLBN_KBC) return fail(XLBN_E_ARG, "stepper_create: unknown collision %d", desc->collision);
+  if (desc->collision == XLBN_KBC && desc->lattice == XLBN_D3Q19)
+    return fail(XLBN_E_UNSUPPORTED, "KBC: velocity set not supported: D3Q19 (reference: kbc.py:71-72, 184-185)");
+  if (desc->compute_dtype != XLBN_F32 && desc->compute_dtype != XLBN_F64) return fail(XLBN_E_DTYPE, "stepper_create: compute dtype %d", desc->compute_dtype);
+  if (!is_float_dtype(desc->store_dtype)) return fail(XLBN_E_DTYPE, "stepper_create: store dtype %d", desc->store_dtype);
+  if (desc->compute_dtype == XLBN_F32 && desc->store_dtype == XLBN_F64) return fail(XLBN_E_DTYPE, "stepper_create: no FP32FP64 policy");
+  if (desc->n_bc < 0 || (desc->n_bc > 0 && !desc->bcs)) return fail(XLBN_E_ARG, "stepper_create: bad BC list");
+  const int cpt = desc->cells_per_thread;
+  if (cpt != 0 && cpt != 1 && cpt != 2 && cpt != 4 && cpt != 8) return fail(XLBN_E_ARG, "stepper_create: cells_per_thread = %d", cpt);
+
+  BcEntry host[256];
+  memset(host, 0, sizeof(host));
+  bool needs_missing = false;
+  for (int i = 0; i < desc->n_bc; ++i) {
+    const xlbn_bc_desc& b = desc->bcs[i];
+    if (b.id < 1 || b.id > 254) return fail(XLBN_E_ARG, "stepper_create: BC id %d outside 1..254", b.id);
+    if (b.kind <= XLBN_BC_NONE || b.kind > XLBN_BC_EXTRAPOLATION_OUTFLOW) return fail(XLBN_E_ARG, "stepper_create: BC kind %d", b.kind);
+    if (host[b.id].kind != 0) return fail(XLBN_E_ARG, "stepper_create: duplicate BC id %d", b.id);
+    host[b.id].kind = b.kind;
+    host[b.id].rho = b.rho;
+    for (int a = 0; a < 3; ++a) host[b.id].u[a] = b.u[a];
+    needs_missing |= bc_kind_needs_missing(b.kind);
+  }
+  xlbn_stepper* s = new xlbn_stepper();
+  s->lattice = desc->lattice;
+  s->collision = desc->collision;
+  s->compute_dtype = desc->compute_dtype;
+  s->store_dtype = desc->store_dtype;
+  s->cells_per_thread = cpt;
+  s->needs_missing = needs_missing;
+  s->table = nullptr;
+  cudaError_t e = cudaGetDevice(&s->device);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->table), sizeof(host));
+  if (e == cudaSuccess) e = cudaMemcpy(s->table, host, sizeof(host), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (s->table) cudaFree(s->table);
+    delete s;
+    return cuda_fail(e, "stepper_create");
+  }
+  *out = s;
+  return 0;
+}
+
+int xlbn_stepper_destroy(xlbn_stepper* s) {
+  if (!s) return 0;
+  if (s->table) cudaFree(s->table);
+  delete s;
+  return 0;
+}
+
+int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask, const uint32_t* missing_bits, const xlbn_domain* dom, double omega,
+              int timestep, xlbn_halo* halo, void* stream) {
+  if (!s || !f0 || !f1 || !bc_mask || !dom) return fail(XLBN_E_ARG, "xlbn_step: NULL argument");
+  if (f0 == f1) return fail(XLBN_E_ARG, "xlbn_step: f0 and f1 must be different buffers (pull scheme)");
+  if (s->needs_missing && !missing_bits) return fail(XLBN_E_ARG, "xlbn_step: this stepper has BCs that read the missing-direction bitmask");
+  if (dom->nx <= 0 || dom->ny <= 0 || dom->nz <= 0) return fail(XLBN_E_SHAPE, "xlbn_step: dims %d %d %d", dom->nx, dom->ny, dom->nz);
+  if (dom->x_begin < 0 || dom->x_count < 0 || dom->x_begin + dom->x_count > dom->nx)
+    return fail(XLBN_E_SHAPE, "xlbn_step: x range [%d, %d) outside [0, %d)", dom->x_begin, dom->x_begin + dom->x_count, dom->nx);
+  if (s->lattice == XLBN_D2Q9 && dom->nz != 1) return fail(XLBN_E_SHAPE, "xlbn_step: 2-D lattice needs nz == 1");
+  if (dom->x_count == 0) return 0;
+
+  StepCall c;
+  c.compute_dtype = s->compute_dtype;
+  c.store_dtype = s->store_dtype;
+  c.requested_v = s->cells_per_thread;
+  c.f0 = f0;
+  c.f1 = f1;
+  c.bc = bc_mask;
+  c.miss = missing_bits;
+  c.table = s->table;
+  c.omega = omega;
+  c.stream = (cudaStream_t)stream;
+  c.ghost_lo = c.ghost_hi = nullptr;
+  c.out_lo = c.out_hi = nullptr;
+  if (s->lattice == XLBN_D2Q9) {  // run [q][nx][ny] as kernel extents (1, nx, ny): unit-stride axis = thread axis
+    if (halo) return fail(XLBN_E_UNSUPPORTED, "xlbn_step: x-slab halo is not available for 2-D lattices");
+    if (dom->x_begin != 0 || dom->x_count != dom->nx) return fail(XLBN_E_UNSUPPORTED, "xlbn_step: partial x range is not available for 2-D lattices");
+    c.nx = 1;
+    c.ny = dom->nx;
+    c.nz = dom->ny;
+    c.x_begin = 0;
+    c.x_count = 1;
+  } else {
+    c.nx = dom->nx;
+    c.ny = dom->ny;
+    c.nz = dom->nz;
+    c.x_begin = dom->x_begin;
+    c.x_count = dom->x_count;
+  }
+  if (halo) {
+    if (!halo->connected) return fail(XLBN_E_STATE, "xlbn_step: halo is not connected");
+    if (halo->lattice != s->lattice || halo->store_dtype != s->store_dtype || halo->ny != dom->ny || halo->nz != dom->nz)
+      return fail(XLBN_E_SHAPE, "xlbn_step: halo does not match the stepper / domain");
+    const int p_in = timestep & 1, p_out = (timestep + 1) & 1;
+    c.ghost_lo = halo_ghost(halo, halo->base, p_in, 0);
+    c.ghost_hi = halo_ghost(halo, halo->base, p_in, 1);
+    c.out_hi = halo_ghost(halo, halo->peer_hi, p_out, 0);
+    c.out_lo = halo_ghost(halo, halo->peer_lo, p_out, 1);
+  }
+  switch (s->lattice) {
+    case XLBN_D3Q19: return dispatch_step<D3Q19, XLBN_BGK>(c);
+    case XLBN_D3Q27: return s->collision == XLBN_BGK ? dispatch_step<D3Q27, XLBN_BGK>(c) : dispatch_step<D3Q27, XLBN_KBC>(c);
+    case XLBN_D2Q9: return s->collision == XLBN_BGK ? dispatch_step<D2Q9, XLBN_BGK>(c) : dispatch_step<D2Q9, XLBN_KBC>(c);
+  }
+  return fail(XLBN_E_ARG, "xlbn_step: bad stepper");
+}
+
+}  // extern "C"

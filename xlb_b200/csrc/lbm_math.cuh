@@ -1,0 +1,238 @@
+// Per-cell LBM algebra in registers, in the compute dtype TC.  One set of device functions shared by the fused step
+// kernel, the boundary-cell path and the stand-alone operator kernels, so all of them produce the same numbers.
+// The operation ORDER follows the reference's Warp functionals (sequential in l), cited per function.
+#pragma once
+
+#include "lattice.cuh"
+
+namespace xlbn {
+
+#define XLBN_DEV __device__ __forceinline__
+#define XLBN_FOR(N, var) static_for<N>([&](auto var##_) { constexpr int var = decltype(var##_)::value;
+#define XLBN_END });
+
+// rho = sum_l f_l ; u_d = (sum_{c=+1} f - sum_{c=-1} f) / rho
+// (reference: zero_moment.py:32-37, first_moment.py:26-38, macroscopic.py:43-47)
+template <class L, class TC>
+XLBN_DEV void macroscopic(const TC (&f)[L::Q], TC& rho, TC (&u)[L::D]) {
+  rho = TC(0);
+  XLBN_FOR(L::Q, l) rho += f[l]; XLBN_END
+  XLBN_FOR(L::D, d) u[d] = TC(0); XLBN_END
+  XLBN_FOR(L::Q, l)
+    XLBN_FOR(L::D, d)
+      if constexpr (L::c(d, l) == 1) u[d] += f[l];
+      else if constexpr (L::c(d, l) == -1) u[d] -= f[l];
+    XLBN_END
+  XLBN_END
+  XLBN_FOR(L::D, d) u[d] /= rho; XLBN_END
+}
+
+// feq_l = rho w_l (1 + cu (1 + 0.5 cu) - usqr), cu = 3 c_l.u, usqr = 1.5 u.u
+// (reference: quadratic_equilibrium.py:35-60)
+template <class L, class TC>
+XLBN_DEV void equilibrium(TC rho, const TC (&u)[L::D], TC (&feq)[L::Q]) {
+  TC uu = TC(0);
+  XLBN_FOR(L::D, d) uu += u[d] * u[d]; XLBN_END
+  const TC usqr = TC(1.5) * uu;
+  XLBN_FOR(L::Q, l)
+    TC cu = TC(0);
+    XLBN_FOR(L::D, d)
+      if constexpr (L::c(d, l) == 1) cu += u[d];
+      else if constexpr (L::c(d, l) == -1) cu -= u[d];
+    XLBN_END
+    cu *= TC(3.0);
+    feq[l] = rho * TC(L::w(l)) * (TC(1.0) + cu * (TC(1.0) + TC(0.5) * cu) - usqr);
+  XLBN_END
+}
+
+// Pi_t = sum_l cc[l][t] f_l   (reference: second_moment.py:67-78)
+template <class L, class TC>
+XLBN_DEV void second_moment(const TC (&f)[L::Q], TC (&pi)[L::NT]) {
+  XLBN_FOR(L::NT, t)
+    pi[t] = TC(0);
+    XLBN_FOR(L::Q, l)
+      if constexpr (L::cc(l, t) == 1) pi[t] += f[l];
+      else if constexpr (L::cc(l, t) == -1) pi[t] -= f[l];
+    XLBN_END
+  XLBN_END
+}
+
+// BGK: f - omega (f - feq)   (reference: bgk.py:30-34)
+template <class L, class TC>
+XLBN_DEV void collide_bgk(const TC (&f)[L::Q], const TC (&feq)[L::Q], TC omega, TC (&out)[L::Q]) {
+  XLBN_FOR(L::Q, l)
+    const TC fneq = f[l] - feq[l];
+    out[l] = f[l] - omega * fneq;
+  XLBN_END
+}
+
+// KBC shear part of fneq (reference: kbc.py:188-250).  s_l for the D3Q27 / D2Q9 lattices.
+template <class L, class TC>
+XLBN_DEV void kbc_shear(const TC (&fneq)[L::Q], TC (&s)[L::Q]) {
+  TC pi[L::NT];
+  second_moment<L, TC>(fneq, pi);
+  XLBN_FOR(L::Q, l) s[l] = TC(0); XLBN_END
+  if constexpr (L::ID == XLBN_D3Q27) {
+    const TC nxz = pi[0] - pi[5];
+    const TC nyz = pi[3] - pi[5];
+    s[9] = (TC(2.0) * nxz - nyz) / TC(6.0);
+    s[18] = s[9];
+    s[3] = (-nxz + TC(2.0) * nyz) / TC(6.0);
+    s[6] = s[3];
+    s[1] = (-nxz - nyz) / TC(6.0);
+    s[2] = s[1];
+    s[12] = pi[1] / TC(4.0);
+    s[24] = s[12];
+    s[21] = -pi[1] / TC(4.0);
+    s[15] = s[21];
+    s[10] = pi[2] / TC(4.0);
+    s[20] = s[10];
+    s[19] = -pi[2] / TC(4.0);
+    s[11] = s[19];
+    s[8] = pi[4] / TC(4.0);
+    s[4] = s[8];
+    s[7] = -pi[4] / TC(4.0);
+    s[5] = s[7];
+  } else if constexpr (L::ID == XLBN_D2Q9) {
+    const TC n = pi[0] - pi[2];
+    s[3] = n;
+    s[6] = n;
+    s[2] = -n;
+    s[1] = -n;
+    s[8] = pi[1];
+    s[4] = -pi[1];
+    s[5] = -pi[1];
+    s[7] = pi[1];
+  }
+}
+
+// KBC (reference: kbc.py:268-296): entropic stabiliser gamma from the scalar products <dh|ds>, <dh|dh> weighted by 1/feq.
+template <class L, class TC>
+XLBN_DEV void collide_kbc(const TC (&f)[L::Q], const TC (&feq)[L::Q], TC rho, TC omega, TC (&out)[L::Q]) {
+  TC fneq[L::Q], ds[L::Q];
+  XLBN_FOR(L::Q, l) fneq[l] = f[l] - feq[l]; XLBN_END
+  kbc_shear<L, TC>(fneq, ds);
+  XLBN_FOR(L::Q, l)
+    if constexpr (L::D == 3) ds[l] = ds[l] * rho;
+    else ds[l] = ds[l] * rho / TC(4.0);
+  XLBN_END
+  const TC beta = TC(0.5) * omega;
+  const TC inv_beta = TC(1.0) / beta;
+  TC sp1 = TC(0), sp2 = TC(0);
+  XLBN_FOR(L::Q, l)
+    const TC dh = fneq[l] - ds[l];
+    const TC temp = dh / feq[l];
+    sp1 += temp * ds[l];
+    sp2 += temp * dh;
+  XLBN_END
+  const TC gamma = inv_beta - (TC(2.0) - inv_beta) * sp1 / (TC(1e-32) + sp2);
+  XLBN_FOR(L::Q, l)
+    const TC dh = fneq[l] - ds[l];
+    out[l] = f[l] - beta * (TC(2.0) * ds[l] + gamma * dh);
+  XLBN_END
+}
+
+// macroscopic -> equilibrium -> collision on one cell, in place (reference: nse_stepper.py:369-371).
+template <class L, int COLL, class TC>
+XLBN_DEV void collide_cell(TC (&f)[L::Q], TC omega) {
+  TC rho, u[L::D], feq[L::Q], out[L::Q];
+  macroscopic<L, TC>(f, rho, u);
+  equilibrium<L, TC>(rho, u, feq);
+  if constexpr (COLL == XLBN_BGK) collide_bgk<L, TC>(f, feq, omega, out);
+  else collide_kbc<L, TC>(f, feq, rho, omega, out);
+  XLBN_FOR(L::Q, l) f[l] = out[l]; XLBN_END
+}
+
+// ---- boundary-condition functionals -------------------------------------------------------------------------------
+// `miss` bit l <=> missing_mask[l, cell].
+
+// First missing axis-aligned direction in index order gives the outward normal n = -c_l
+// (reference: helper_functions_bc.py:75-86, bc_extrapolation_outflow.py:139-149).
+template <class L>
+XLBN_DEV void bc_normal(uint32_t miss, int (&n)[L::D]) {
+  bool found = false;
+  XLBN_FOR(L::D, d) n[d] = 0; XLBN_END
+  XLBN_FOR(L::Q, l)
+    if constexpr (L::is_main(l)) {
+      if (!found && ((miss >> l) & 1u)) {
+        found = true;
+        XLBN_FOR(L::D, d) n[d] = -L::c(d, l); XLBN_END
+      }
+    }
+  XLBN_END
+}
+
+// fsum = 2 sum_known f + sum_middle f; known: missing[opp[l]], middle: neither (reference: helper_functions_bc.py:61-73)
+template <class L, class TC>
+XLBN_DEV TC bc_fsum(const TC (&f)[L::Q], uint32_t miss) {
+  TC known = TC(0), middle = TC(0);
+  XLBN_FOR(L::Q, l)
+    if ((miss >> L::opp(l)) & 1u) known += TC(2.0) * f[l];
+    else if (!((miss >> l) & 1u)) middle += f[l];
+  XLBN_END
+  return known + middle;
+}
+
+// missing l (sequential, in place): f[l] = f[opp[l]] + feq[l] - feq[opp[l]]  (reference: helper_functions_bc.py:88-97)
+template <class L, class TC>
+XLBN_DEV void bc_bounceback_nonequilibrium(TC (&f)[L::Q], const TC (&feq)[L::Q], uint32_t miss) {
+  XLBN_FOR(L::Q, l)
+    if ((miss >> l) & 1u) f[l] = f[L::opp(l)] + feq[l] - feq[L::opp(l)];
+  XLBN_END
+}
+
+// all l: f[l] = feq[l] + 4.5 w_l (Q_l : Pi_neq)   (reference: helper_functions_bc.py:99-122)
+template <class L, class TC>
+XLBN_DEV void bc_regularize(TC (&f)[L::Q], const TC (&feq)[L::Q]) {
+  TC fneq[L::Q], pi[L::NT];
+  XLBN_FOR(L::Q, l) fneq[l] = f[l] - feq[l]; XLBN_END
+  second_moment<L, TC>(fneq, pi);
+  XLBN_FOR(L::Q, l)
+    TC qipi = TC(0);
+    XLBN_FOR(L::NT, t) qipi += TC(L::qi(l, t)) * pi[t]; XLBN_END
+    f[l] = feq[l] + TC(4.5) * TC(L::w(l)) * qipi;
+  XLBN_END
+}
+
+// Zou-He / Regularized on the post-stream populations (reference: bc_zouhe.py:279-338, bc_regularized.py:134-202).
+// `aux` is the per-cell prescribed scalar: normal velocity magnitude (velocity type) or density (pressure type).
+template <class L, class TC>
+XLBN_DEV void bc_zouhe(int kind, TC aux, uint32_t miss, TC (&f)[L::Q]) {
+  int ni[L::D];
+  bc_normal<L>(miss, ni);
+  TC nrm[L::D], u[L::D], feq[L::Q];
+  XLBN_FOR(L::D, d) nrm[d] = TC(ni[d]); XLBN_END
+  const TC fsum = bc_fsum<L, TC>(f, miss);
+  TC rho;
+  if (kind == XLBN_BC_ZOUHE_VELOCITY || kind == XLBN_BC_REGULARIZED_VELOCITY) {
+    TC unormal = TC(0);
+    XLBN_FOR(L::D, d) u[d] = -aux * nrm[d]; XLBN_END
+    XLBN_FOR(L::D, d) unormal += u[d] * nrm[d]; XLBN_END
+    rho = fsum / (TC(1.0) + unormal);
+  } else {
+    rho = aux;
+    const TC unormal = -TC(1.0) + fsum / rho;
+    XLBN_FOR(L::D, d) u[d] = unormal * nrm[d]; XLBN_END
+  }
+  equilibrium<L, TC>(rho, u, feq);
+  bc_bounceback_nonequilibrium<L, TC>(f, feq, miss);
+  if (kind == XLBN_BC_REGULARIZED_VELOCITY || kind == XLBN_BC_REGULARIZED_PRESSURE) bc_regularize<L, TC>(f, feq);
+}
+
+// missing l: f[l] = f_pre[opp[l]]   (reference: bc_halfway_bounce_back.py:68-85, bc_extrapolation_outflow.py:152-170)
+template <class L, class TC>
+XLBN_DEV void bc_take_opposite_of_pre(const TC (&fpre)[L::Q], uint32_t miss, TC (&f)[L::Q]) {
+  XLBN_FOR(L::Q, l)
+    if ((miss >> l) & 1u) f[l] = fpre[L::opp(l)];
+  XLBN_END
+}
+
+inline __host__ __device__ bool bc_kind_needs_aux(int kind) { return kind >= XLBN_BC_ZOUHE_VELOCITY && kind <= XLBN_BC_REGULARIZED_PRESSURE; }
+inline __host__ __device__ bool bc_kind_needs_fpre(int kind) {
+  return kind == XLBN_BC_DO_NOTHING || kind == XLBN_BC_HALFWAY_BOUNCE_BACK || kind == XLBN_BC_EXTRAPOLATION_OUTFLOW;
+}
+inline __host__ __device__ bool bc_kind_needs_missing(int kind) {
+  return kind == XLBN_BC_HALFWAY_BOUNCE_BACK || kind >= XLBN_BC_ZOUHE_VELOCITY;
+}
+
+}  // namespace xlbn

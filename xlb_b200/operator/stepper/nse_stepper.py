@@ -1,0 +1,227 @@
+"""IncompressibleNavierStokesStepper: ONE fused CUDA kernel per lattice-Boltzmann time step.
+
+Reference: xlb/operator/stepper/nse_stepper.py — ctor L26-56, prepare_fields L58-98, mask / aux set-up L100-135, JAX
+pull step L147-192, Warp fused kernel L344-381 and its launch L385-392.
+
+The step is `xlbn_step` (include/xlb_b200.h; kernel in xlb_b200/csrc/step_kernel.cuh): pull-stream -> streaming BCs ->
+macroscopic -> equilibrium -> BGK/KBC -> collision BCs / outflow aux -> aux recovery -> store, selected per cell through
+the uint8 ``bc_mask``.  Call signature is the reference's for both conventions:
+``stepper(f_0, f_1, bc_mask, missing_mask, omega, timestep) -> (f_0, f_1)``; the caller swaps the buffers.
+
+Differences from the reference that are visible to a caller: none in the fields.  Internally the bool ``missing_mask``
+[q, ...] is packed once into a uint32 bitmask that only boundary cells read, and on an x-slab grid (torch.distributed,
+one process per GPU) the halo exchange is fused into the step (xlb_b200/distribute/halo.py).
+"""
+
+import ctypes as C
+
+import torch
+
+from xlb_b200 import native
+from xlb_b200.compute_backend import ComputeBackend
+from xlb_b200.default_config import DefaultConfig
+from xlb_b200.helper.check_boundary_overlaps import check_bc_overlaps
+from xlb_b200.helper.nse_solver import create_nse_fields
+from xlb_b200.operator.boundary_condition.boundary_condition import ImplementationStep
+from xlb_b200.operator.boundary_masker import IndicesBoundaryMasker
+from xlb_b200.operator.collision import BGK, KBC
+from xlb_b200.operator.equilibrium import QuadraticEquilibrium
+from xlb_b200.operator.macroscopic import Macroscopic
+from xlb_b200.operator.operator import Operator
+from xlb_b200.operator.stepper.stepper import Stepper
+from xlb_b200.operator.stream import Stream
+
+
+class IncompressibleNavierStokesStepper(Stepper):
+    def __init__(
+        self,
+        grid,
+        boundary_conditions=[],
+        collision_type="BGK",
+        streaming_scheme="pull",
+        forcing_scheme="exact_difference",
+        force_vector=None,
+        cells_per_thread=0,
+    ):
+        super().__init__(grid, boundary_conditions)
+        if collision_type == "BGK":
+            self.collision = BGK(self.velocity_set, self.precision_policy, self.compute_backend)
+        elif collision_type == "KBC":
+            self.collision = KBC(self.velocity_set, self.precision_policy, self.compute_backend)
+        else:
+            raise NotImplementedError(f"collision_type = {collision_type!r} is outside the scope of this backend (BGK, KBC)")
+        if force_vector is not None:
+            raise NotImplementedError("body forces (ForcedCollision / ExactDifference) are outside the scope of this backend")
+        self.collision_type = collision_type
+        self.streaming_scheme = streaming_scheme
+        if streaming_scheme != "pull":
+            raise NotImplementedError(f"Unknown or unimplemented streaming scheme for this backend: {streaming_scheme}")
+
+        self.stream = Stream(self.velocity_set, self.precision_policy, self.compute_backend)
+        self.equilibrium = QuadraticEquilibrium(self.velocity_set, self.precision_policy, self.compute_backend)
+        self.macroscopic = Macroscopic(self.velocity_set, self.precision_policy, self.compute_backend)
+
+        self.cells_per_thread = int(cells_per_thread)
+        self._handle = None
+        self._handle_key = None
+        self._bits = None
+        self._bits_key = None
+        self._halo = None
+        self._halo_step = 0
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                native.lib().xlbn_stepper_destroy(self._handle)
+        except Exception:
+            pass
+
+    # -- set-up (host + a few one-off kernels) ---------------------------------------------------------------------
+    def prepare_fields(self, initializer=None):
+        """Returns (f_0, f_1, bc_mask, missing_mask) — reference: nse_stepper.py:58-98."""
+        _, f_0, f_1, missing_mask, bc_mask = create_nse_fields(
+            grid=self.grid, velocity_set=self.velocity_set, compute_backend=self.compute_backend, precision_policy=self.precision_policy
+        )
+        if initializer is not None:
+            f_0 = initializer(self.grid, self.velocity_set, self.precision_policy, self.compute_backend)
+        else:
+            from xlb_b200.helper.initializers import initialize_eq
+
+            f_0 = initialize_eq(f_0, self.grid, self.velocity_set, self.precision_policy, self.compute_backend)
+        f_1.copy_(f_0)
+        bc_mask, missing_mask = self._process_boundary_conditions(self.boundary_conditions, bc_mask, missing_mask, grid=self.grid)
+        f_0, f_1 = self._initialize_auxiliary_data(self.boundary_conditions, f_0, f_1, bc_mask, missing_mask, grid=self.grid)
+        return f_0, f_1, bc_mask, missing_mask
+
+    @classmethod
+    def _process_boundary_conditions(cls, boundary_conditions, bc_mask, missing_mask, grid=None):
+        check_bc_overlaps(boundary_conditions, DefaultConfig.velocity_set.d, DefaultConfig.default_backend)
+        if any(bc.mesh_vertices is not None for bc in boundary_conditions):
+            raise NotImplementedError("mesh-based boundary conditions (MeshBoundaryMasker) are outside the scope of this backend")
+        masker = IndicesBoundaryMasker(
+            velocity_set=DefaultConfig.velocity_set,
+            precision_policy=DefaultConfig.default_precision_policy,
+            compute_backend=DefaultConfig.default_backend,
+        )
+        bc_with_indices = [bc for bc in boundary_conditions if bc.indices is not None]
+        if bc_with_indices:
+            kw = {}
+            if grid is not None and grid.nDevices > 1:
+                kw = dict(start_index=grid.start_index, global_shape=grid.shape)
+            bc_mask, missing_mask = masker(bc_with_indices, bc_mask, missing_mask, **kw)
+        return bc_mask, missing_mask
+
+    @staticmethod
+    def _initialize_auxiliary_data(boundary_conditions, f_0, f_1, bc_mask, missing_mask, grid=None):
+        for bc in boundary_conditions:
+            if bc.needs_aux_init and not bc.is_initialized_with_aux_data:
+                kw = {}
+                if grid is not None:
+                    kw = dict(start_index=grid.start_index, global_shape=grid.shape)
+                f_0, f_1 = bc.aux_data_init(f_0, f_1, bc_mask, missing_mask, **kw)
+        return f_0, f_1
+
+    # -- native handle ---------------------------------------------------------------------------------------------------
+    def _native_handle(self):
+        descs = [bc.native_desc() for bc in self.boundary_conditions]
+        key = tuple((d.id, d.kind, d.rho, d.u[0], d.u[1], d.u[2]) for d in descs) + (self.cells_per_thread,)
+        if self._handle is not None and key == self._handle_key:
+            return self._handle
+        if self._handle is not None:
+            native.lib().xlbn_stepper_destroy(self._handle)
+            self._handle = None
+        arr = (native.BcDesc * max(1, len(descs)))(*descs)
+        desc = native.StepperDesc(
+            lattice=self._lattice,
+            collision=self.collision.native_collision,
+            compute_dtype=self.precision_policy.compute_precision.code,
+            store_dtype=self.precision_policy.store_precision.code,
+            n_bc=len(descs),
+            cells_per_thread=self.cells_per_thread,
+            bcs=arr,
+        )
+        out = C.c_void_p()
+        native.check(native.lib().xlbn_stepper_create(C.byref(desc), C.byref(out)))
+        self._handle, self._handle_key = out, key
+        self._needs_missing = any(d.kind in (native.BC_HALFWAY_BOUNCE_BACK,) or d.kind >= native.BC_ZOUHE_VELOCITY for d in descs)
+        return self._handle
+
+    def _missing_bits(self, missing_mask):
+        """uint32 bitmask [cells], bit l = missing_mask[l, cell]; packed once per mask (re-packed if it is modified)."""
+        key = (missing_mask.data_ptr(), missing_mask._version, tuple(missing_mask.shape))
+        if self._bits is None or self._bits_key != key:
+            native.require_cuda(missing_mask, "missing_mask")
+            if missing_mask.dtype != torch.bool or missing_mask.shape[0] != self.velocity_set.q:
+                raise TypeError("missing_mask must be a bool array [q, ...]")
+            n_cells = missing_mask[0].numel()
+            bits = torch.empty(n_cells, dtype=torch.int32, device=missing_mask.device)
+            native.check(native.lib().xlbn_pack_missing(self.velocity_set.q, native.ptr(missing_mask), native.ptr(bits), n_cells, native.stream_of(bits)))
+            self._bits, self._bits_key = bits, key
+        return self._bits
+
+    # -- one time step -----------------------------------------------------------------------------------------------------
+    def _step(self, f_0, f_1, bc_mask, missing_mask, omega, timestep):
+        vs = self.velocity_set
+        for name, t in (("f_0", f_0), ("f_1", f_1), ("bc_mask", bc_mask)):
+            native.require_cuda(t, name)
+        if f_0.dtype != self.store_dtype or f_1.dtype != self.store_dtype:
+            raise TypeError(f"populations must be stored as {self.store_dtype} under {self.precision_policy.name}")
+        if f_0.shape != f_1.shape or f_0.shape[0] != vs.q:
+            raise ValueError(f"f_0 / f_1 must both be [q={vs.q}, ...], got {tuple(f_0.shape)} / {tuple(f_1.shape)}")
+        if bc_mask.dtype != torch.uint8 or bc_mask.shape[1:] != f_0.shape[1:]:
+            raise ValueError("bc_mask must be uint8 [1, ...] matching the populations")
+        nx, ny, nz = native.dims_of(f_0, vs.d)
+        handle = self._native_handle()
+        bits = self._missing_bits(missing_mask) if self._needs_missing else None
+        if self.grid is not None and self.grid.nDevices > 1:
+            return self._step_slab(handle, f_0, f_1, bc_mask, bits, (nx, ny, nz), float(omega))
+        dom = native.Domain(nx, ny, nz, 0, nx)
+        native.check(
+            native.lib().xlbn_step(handle, native.ptr(f_0), native.ptr(f_1), native.ptr(bc_mask), native.ptr(bits), C.byref(dom), float(omega), int(timestep), None, native.stream_of(f_0))
+        )
+        return f_0, f_1
+
+    def _step_slab(self, handle, f_0, f_1, bc_mask, bits, dims, omega):
+        """x-slab step with the halo exchange fused into the kernels of the two face planes and overlapped with the
+        interior update on a second stream (xlb_b200/distribute/halo.py)."""
+        from xlb_b200.distribute.halo import PeerHalo
+
+        if self._halo is None:
+            self._halo = PeerHalo(self.grid, self.velocity_set, self.precision_policy, dims)
+            self._halo_step = 0
+        self._halo.step(handle, f_0, f_1, bc_mask, bits, dims, omega, self._halo_step)
+        self._halo_step += 1
+        return f_0, f_1
+
+    def reset_halo(self):
+        """Re-prime the ghost planes from the populations passed to the next call (use after modifying the populations
+        outside the stepper on a slab grid).  Collective: synchronises the device and all ranks, then skips two halo
+        steps so that stale step counters cannot satisfy the next wait."""
+        if self._halo is not None:
+            import torch.distributed as dist
+
+            torch.cuda.synchronize()
+            dist.barrier()
+            self._halo_step += 2
+            self._halo.primed = False
+
+    def __call__(self, f_0, f_1, bc_mask, missing_mask, omega, timestep=0, callback=None):
+        """Hot loop entry: same contract as Operator.__call__ (errors are re-raised as a generic Exception with the
+        traceback text, reference operator.py:69-74) without the per-call signature matching."""
+        try:
+            result = self._step(f_0, f_1, bc_mask, missing_mask, omega, timestep)
+        except Exception as e:
+            import traceback
+
+            raise Exception(f"Error captured for backend {self.compute_backend} for operator {self.__class__.__name__}: {e}\n {traceback.format_exc()}")
+        if callback and callable(callback):
+            callback(result)
+        return result
+
+    @Operator.register_backend(ComputeBackend.JAX)
+    def jax_implementation(self, f_0, f_1, bc_mask, missing_mask, omega, timestep):
+        return self._step(f_0, f_1, bc_mask, missing_mask, omega, timestep)
+
+    @Operator.register_backend(ComputeBackend.WARP)
+    def warp_implementation(self, f_0, f_1, bc_mask, missing_mask, omega, timestep):
+        return self._step(f_0, f_1, bc_mask, missing_mask, omega, timestep)
