@@ -137,7 +137,10 @@ def native_case(g, backend="WARP", cells_per_thread=0):
         bc.id = b["id"]
         bcs.append(bc)
     stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=bcs, collision_type=g["collision"], cells_per_thread=cells_per_thread)
-    f_init = g["f_init"] if be == ComputeBackend.JAX or len(g["shape"]) == 3 else g["f_init"][..., None]
+    # the reference's JAX path keeps the initial state in the compute dtype; here populations always live in the store dtype
+    f_init = g["f_init"].astype(pp.store_precision.np_dtype)
+    if be == ComputeBackend.WARP and len(g["shape"]) == 2:
+        f_init = f_init[..., None]
 
     def initializer(grid, velocity_set, precision_policy, compute_backend):
         return xlb.field.as_field(torch.as_tensor(np.ascontiguousarray(f_init)), device=grid.device)

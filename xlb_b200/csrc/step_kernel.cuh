@@ -20,6 +20,9 @@
 //    (compute and NVLink transfer in the same kernel; no pack / exchange pass).
 #pragma once
 
+#include <cstring>
+#include <initializer_list>
+
 #include "lbm_math.cuh"
 
 namespace xlbn {
@@ -31,38 +34,114 @@ struct BcEntry {
   double u[3];
 };
 
+constexpr int kMaxQ = 27;
+
+// Kernel parameters.  Everything that depends only on (population, x-plane class) is folded into pointer tables on the
+// host, so that inside the kernel an address is ONE table entry (constant bank) + ONE 32-bit per-thread element offset
+//   off = x * plane + y_src * nz + z_src
+// (2 integer instructions per load/store instead of 64-bit multiplies per population).
+//   pull[0][l] = f0 + l*n - ck0(l)*plane              planes whose x-neighbours are inside the array
+//   pull[1][l] = plane x = 0   : c_x = +1 populations come from ghost_lo (or wrap to plane nx-1)
+//   pull[2][l] = plane x = nx-1: c_x = -1 populations come from ghost_hi (or wrap to plane 0)
+//   push[l]    = f1 + l*n
+//   peer_hi[l] / peer_lo[l]: neighbour GPUs' ghost planes (biased by -x*plane), only for the face populations
 template <class TS>
 struct StepParams {
+  const TS* pull[3][kMaxQ];
+  TS* push[kMaxQ];
+  TS* peer_hi[kMaxQ];  // written by plane nx-1 (c_x = +1 populations) or NULL
+  TS* peer_lo[kMaxQ];  // written by plane 0    (c_x = -1 populations) or NULL
+  const uint8_t* bc;
+  // boundary-cell path only
   const TS* f0;
   TS* f1;
-  TS* f0w;  // writable alias of f0: aux recovery only (nse_stepper.py:338)
-  const uint8_t* bc;
+  TS* f0w;  // writable alias of f0: aux recovery (nse_stepper.py:338)
   const uint32_t* miss;
   const BcEntry* table;  // 256 entries, indexed by bc id
+  const TS* ghost_lo;    // plane "x = -1": populations with ck(0) = +1, [n_xdir][ny][nz]; NULL -> periodic wrap
+  const TS* ghost_hi;    // plane "x = nx"
   int nx, ny, nz, x_begin;
   long long plane;  // ny * nz
   long long n;      // nx * ny * nz  (population stride)
   double omega;
-  const TS* ghost_lo;  // plane "x = -1":  populations with ck(0) = +1, [n_xdir][ny][nz]; NULL -> periodic wrap
-  const TS* ghost_hi;  // plane "x = nx":  populations with ck(0) = -1
-  TS* out_lo;          // lo neighbour's ghost_hi for the NEXT step (peer memory) or NULL
-  TS* out_hi;          // hi neighbour's ghost_lo for the NEXT step (peer memory) or NULL
 };
 
-// Start of x-plane (x - cx) of population l as seen by a pull: inside the array, in a ghost plane, or wrapped.
-template <class L, class TS, int l>
-XLBN_DEV const TS* pull_plane(const StepParams<TS>& p, int x) {
-  constexpr int cx = L::ck(0, l);
-  const TS* base = p.f0 + (long long)l * p.n;
-  if constexpr (cx == 0) {
-    return base + (long long)x * p.plane;
-  } else if constexpr (cx == 1) {
-    if (x > 0) return base + (long long)(x - 1) * p.plane;
-    return p.ghost_lo ? p.ghost_lo + (long long)L::xdir_slot(l) * p.plane : base + (long long)(p.nx - 1) * p.plane;
-  } else {
-    if (x < p.nx - 1) return base + (long long)(x + 1) * p.plane;
-    return p.ghost_hi ? p.ghost_hi + (long long)L::xdir_slot(l) * p.plane : base;
+// ---- explicit global-space memory instructions (SASS: LDG / STG; the compiler cannot prove the address space of
+//      pointers that arrive inside a parameter struct and would emit generic LD / ST) --------------------------------
+template <int BYTES>
+struct GMem;
+template <>
+struct GMem<1> {
+  using T = uint8_t;
+  static XLBN_DEV T ld(const void* p) {
+    uint32_t v;
+    asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return (T)v;
   }
+  static XLBN_DEV void st(void* p, T v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"((uint32_t)v) : "memory"); }
+};
+template <>
+struct GMem<2> {
+  using T = uint16_t;
+  static XLBN_DEV T ld(const void* p) {
+    T v;
+    asm volatile("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return v;
+  }
+  static XLBN_DEV void st(void* p, T v) { asm volatile("st.global.u16 [%0], %1;" ::"l"(p), "h"(v) : "memory"); }
+};
+template <>
+struct GMem<4> {
+  using T = uint32_t;
+  static XLBN_DEV T ld(const void* p) {
+    T v;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+  }
+  static XLBN_DEV void st(void* p, T v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+};
+template <>
+struct GMem<8> {
+  using T = uint2;
+  static XLBN_DEV T ld(const void* p) {
+    T v;
+    asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+  }
+  static XLBN_DEV void st(void* p, T v) { asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory"); }
+};
+template <>
+struct GMem<16> {
+  using T = uint4;
+  static XLBN_DEV T ld(const void* p) {
+    T v;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+  }
+  static XLBN_DEV void st(void* p, T v) {
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+};
+
+template <class T, int V>
+XLBN_DEV Pack<T, V> gload(const T* p) {
+  using G = GMem<(int)sizeof(T) * V>;
+  union {
+    typename G::T raw;
+    Pack<T, V> pack;
+  } u;
+  u.raw = G::ld(p);
+  return u.pack;
+}
+template <class T, int V>
+XLBN_DEV void gstore(T* p, const Pack<T, V>& x) {
+  using G = GMem<(int)sizeof(T) * V>;
+  union {
+    typename G::T raw;
+    Pack<T, V> pack;
+  } u;
+  u.pack = x;
+  G::st(p, u.raw);
 }
 
 // f0[l] at an arbitrary (possibly out-of-range) kernel-coordinate cell: periodic in y/z; x through ghost or wrap.
@@ -147,95 +226,95 @@ __device__ __noinline__ void bc_cell(const StepParams<TS>& p, int id, int x, int
 template <class L, int COLL, class TC, class TS, int V>
 struct StepTraits {
   static constexpr int kThreads = 128;
-  // register estimate: V*Q population registers (x2 for fp64) + algebra temporaries
-  static constexpr int kRegs = V * L::Q * (int)(sizeof(TC) / 4) + (COLL == XLBN_KBC ? 3 * L::Q * (int)(sizeof(TC) / 4) : 40) + 24;
+  // register budget: V*Q population registers (x2 for fp64) + algebra temporaries and addresses
+  static constexpr int kRegs = V * L::Q * (int)(sizeof(TC) / 4) + (COLL == XLBN_KBC ? 2 * L::Q * (int)(sizeof(TC) / 4) : 24) + 24;
   static constexpr int kMinBlocksRaw = 65536 / (kThreads * (kRegs > 255 ? 255 : kRegs));
   static constexpr int kMinBlocks = kMinBlocksRaw < 1 ? 1 : (kMinBlocksRaw > 12 ? 12 : kMinBlocksRaw);
 };
 
-template <class L, int COLL, class TC, class TS, int V>
-__global__ void __launch_bounds__(StepTraits<L, COLL, TC, TS, V>::kThreads, StepTraits<L, COLL, TC, TS, V>::kMinBlocks)
-    step_kernel(const __grid_constant__ StepParams<TS> p) {
+// XC = x-plane class of this block: 0 interior, 1 plane 0, 2 plane nx-1, 3 both (nx == 1)
+template <class L, int COLL, class TC, class TS, int V, int XC>
+XLBN_DEV void step_body(const StepParams<TS>& p, const int x, const int y, const int z0) {
   constexpr int Q = L::Q;
-  const int zv = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  const int x = p.x_begin + blockIdx.z;
-  const int z0 = zv * V;
-  if (z0 >= p.nz || y >= p.ny) return;
-
-  const int nz = p.nz;
-  const long long cell = (long long)x * p.plane + (long long)y * nz + z0;
+  const unsigned nz = (unsigned)p.nz;
+  const unsigned xoff = (unsigned)x * (unsigned)p.plane;
+  // rows the pull reads from: y - cy with periodic wrap (stream.py:66-78); element offsets inside the population
+  const unsigned row_c = xoff + (unsigned)y * nz;
+  const unsigned row_m = xoff + (unsigned)(y == 0 ? p.ny - 1 : y - 1) * nz;  // source row for cy = +1
+  const unsigned row_p = xoff + (unsigned)(y == p.ny - 1 ? 0 : y + 1) * nz;  // source row for cy = -1
+  const unsigned z_lo = (z0 == 0) ? nz - 1 : (unsigned)z0 - 1;                 // element left of the vector  (cz = +1)
+  const unsigned z_hi = ((unsigned)z0 + V >= nz) ? 0u : (unsigned)z0 + V;      // element right of the vector (cz = -1)
+  const unsigned cell = row_c + (unsigned)z0;
 
   // boundary ids of the V cells (one V-byte load)
-  const Pack<uint8_t, V> ids = load_pack<uint8_t, V>(p.bc + cell);
-  bool any_solid = false, all_solid = true;
+  const Pack<uint8_t, V> ids = gload<uint8_t, V>(p.bc + cell);
+  bool any_solid = false, all_solid = true, any_bc = false;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     any_solid |= (ids.v[v] == 255);
     all_solid &= (ids.v[v] == 255);
+    any_bc |= (ids.v[v] != 0);
   }
   if (all_solid) return;  // nse_stepper.py:356-358
 
-  // rows the pull reads from: y - cy with periodic wrap (stream.py:66-78)
-  const long long row_c = (long long)y * nz;
-  const long long row_m = (long long)(y == 0 ? p.ny - 1 : y - 1) * nz;   // source row for cy = +1
-  const long long row_p = (long long)(y == p.ny - 1 ? 0 : y + 1) * nz;   // source row for cy = -1
-  const int z_lo = (z0 == 0) ? nz - 1 : z0 - 1;                           // element left of the vector  (cz = +1)
-  const int z_hi = (z0 + V >= nz) ? 0 : z0 + V;                           // element right of the vector (cz = -1)
-
   TC f[V][Q];
   XLBN_FOR(Q, l)
-    constexpr int cy = L::ck(1, l), cz = L::ck(2, l);
-    const TS* row = pull_plane<L, TS, l>(p, x) + (cy == 1 ? row_m : (cy == -1 ? row_p : row_c));
+    constexpr int cx = L::ck(0, l), cy = L::ck(1, l), cz = L::ck(2, l);
+    constexpr int tab = (cx == 1 && (XC & 1)) ? 1 : ((cx == -1 && (XC & 2)) ? 2 : 0);
+    const TS* base = p.pull[tab][l];
+    const unsigned row = (cy == 1 ? row_m : (cy == -1 ? row_p : row_c));
     if constexpr (cz == 0) {
-      const Pack<TS, V> a = load_pack<TS, V>(row + z0);
+      const Pack<TS, V> a = gload<TS, V>(base + (row + (unsigned)z0));
 #pragma unroll
       for (int v = 0; v < V; ++v) f[v][l] = Cvt<TC, TS>::up(a.v[v]);
     } else if constexpr (V == 1) {
-      f[0][l] = Cvt<TC, TS>::up(row[cz == 1 ? z_lo : z_hi]);
+      const Pack<TS, 1> a = gload<TS, 1>(base + (row + (cz == 1 ? z_lo : z_hi)));
+      f[0][l] = Cvt<TC, TS>::up(a.v[0]);
     } else if constexpr (cz == 1) {  // out[z] = in[z - 1]
-      const Pack<TS, V> a = load_pack<TS, V>(row + z0);
-      const TS e = row[z_lo];
-      f[0][l] = Cvt<TC, TS>::up(e);
+      const Pack<TS, V> a = gload<TS, V>(base + (row + (unsigned)z0));
+      const Pack<TS, 1> e = gload<TS, 1>(base + (row + z_lo));
+      f[0][l] = Cvt<TC, TS>::up(e.v[0]);
 #pragma unroll
       for (int v = 1; v < V; ++v) f[v][l] = Cvt<TC, TS>::up(a.v[v - 1]);
     } else {  // out[z] = in[z + 1]
-      const Pack<TS, V> a = load_pack<TS, V>(row + z0);
-      const TS e = row[z_hi];
+      const Pack<TS, V> a = gload<TS, V>(base + (row + (unsigned)z0));
+      const Pack<TS, 1> e = gload<TS, 1>(base + (row + z_hi));
 #pragma unroll
       for (int v = 0; v < V - 1; ++v) f[v][l] = Cvt<TC, TS>::up(a.v[v + 1]);
-      f[V - 1][l] = Cvt<TC, TS>::up(e);
+      f[V - 1][l] = Cvt<TC, TS>::up(e.v[0]);
     }
   XLBN_END
 
   const TC omega = (TC)p.omega;
+  if (!any_bc) {
 #pragma unroll
-  for (int v = 0; v < V; ++v) {
-    const int id = ids.v[v];
-    if (id == 0) {
-      collide_cell<L, COLL, TC>(f[v], omega);
-    } else if (id != 255) {
-      TC tmp[Q];
-      XLBN_FOR(Q, l) tmp[l] = f[v][l]; XLBN_END
-      bc_cell<L, COLL, TC, TS>(p, id, x, y, z0 + v, tmp);
-      XLBN_FOR(Q, l) f[v][l] = tmp[l]; XLBN_END
+    for (int v = 0; v < V; ++v) collide_cell<L, COLL, TC>(f[v], omega);
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int id = ids.v[v];
+      if (id == 0) {
+        collide_cell<L, COLL, TC>(f[v], omega);
+      } else if (id != 255) {
+        TC tmp[Q];
+        XLBN_FOR(Q, l) tmp[l] = f[v][l]; XLBN_END
+        bc_cell<L, COLL, TC, TS>(p, id, x, y, z0 + v, tmp);
+        XLBN_FOR(Q, l) f[v][l] = tmp[l]; XLBN_END
+      }
     }
   }
 
   // store (fused compute -> store conversion); outgoing face populations also go to the neighbour GPUs' ghost planes
-  const bool to_hi = (p.out_hi != nullptr) && (x == p.nx - 1);
-  const bool to_lo = (p.out_lo != nullptr) && (x == 0);
-  const long long yz = row_c + z0;
   if (!any_solid) {
     XLBN_FOR(Q, l)
       Pack<TS, V> a;
 #pragma unroll
       for (int v = 0; v < V; ++v) a.v[v] = Cvt<TC, TS>::down(f[v][l]);
-      store_pack<TS, V>(p.f1 + (long long)l * p.n + cell, a);
-      if constexpr (L::ck(0, l) == 1) {
-        if (to_hi) store_pack<TS, V>(p.out_hi + (long long)L::xdir_slot(l) * p.plane + yz, a);
-      } else if constexpr (L::ck(0, l) == -1) {
-        if (to_lo) store_pack<TS, V>(p.out_lo + (long long)L::xdir_slot(l) * p.plane + yz, a);
+      gstore<TS, V>(p.push[l] + cell, a);
+      if constexpr (L::ck(0, l) == 1 && (XC & 2)) {
+        if (p.peer_hi[l]) gstore<TS, V>(p.peer_hi[l] + cell, a);
+      } else if constexpr (L::ck(0, l) == -1 && (XC & 1)) {
+        if (p.peer_lo[l]) gstore<TS, V>(p.peer_lo[l] + cell, a);
       }
     XLBN_END
   } else {
@@ -243,16 +322,33 @@ __global__ void __launch_bounds__(StepTraits<L, COLL, TC, TS, V>::kThreads, Step
     for (int v = 0; v < V; ++v) {
       if (ids.v[v] == 255) continue;
       XLBN_FOR(Q, l)
-        const TS s = Cvt<TC, TS>::down(f[v][l]);
-        p.f1[(long long)l * p.n + cell + v] = s;
-        if constexpr (L::ck(0, l) == 1) {
-          if (to_hi) p.out_hi[(long long)L::xdir_slot(l) * p.plane + yz + v] = s;
-        } else if constexpr (L::ck(0, l) == -1) {
-          if (to_lo) p.out_lo[(long long)L::xdir_slot(l) * p.plane + yz + v] = s;
+        Pack<TS, 1> a;
+        a.v[0] = Cvt<TC, TS>::down(f[v][l]);
+        gstore<TS, 1>(p.push[l] + (cell + v), a);
+        if constexpr (L::ck(0, l) == 1 && (XC & 2)) {
+          if (p.peer_hi[l]) gstore<TS, 1>(p.peer_hi[l] + (cell + v), a);
+        } else if constexpr (L::ck(0, l) == -1 && (XC & 1)) {
+          if (p.peer_lo[l]) gstore<TS, 1>(p.peer_lo[l] + (cell + v), a);
         }
       XLBN_END
     }
   }
+}
+
+template <class L, int COLL, class TC, class TS, int V>
+__global__ void __launch_bounds__(StepTraits<L, COLL, TC, TS, V>::kThreads, StepTraits<L, COLL, TC, TS, V>::kMinBlocks)
+    step_kernel(const __grid_constant__ StepParams<TS> p) {
+  const int zv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x = p.x_begin + blockIdx.z;
+  const int z0 = zv * V;
+  if (z0 >= p.nz || y >= p.ny) return;
+  // block-uniform dispatch on the x-plane class: interior planes carry no ghost / wrap logic at all
+  const bool first = (x == 0), last = (x == p.nx - 1);
+  if (!first && !last) step_body<L, COLL, TC, TS, V, 0>(p, x, y, z0);
+  else if (first && !last) step_body<L, COLL, TC, TS, V, 1>(p, x, y, z0);
+  else if (last && !first) step_body<L, COLL, TC, TS, V, 2>(p, x, y, z0);
+  else step_body<L, COLL, TC, TS, V, 3>(p, x, y, z0);
 }
 
 // ---- host-side launch ------------------------------------------------------------------------------------------------
@@ -272,28 +368,27 @@ int launch_step_v(const StepParams<TS>& p, int x_count, cudaStream_t stream) {
 }
 
 // V must divide nz and keep every vector access aligned; otherwise fall back to the next smaller V.
-template <class TS>
-int pick_cells_per_thread(int requested, int dflt, const StepParams<TS>& p) {
+inline int pick_cells_per_thread(int requested, int dflt, int esize, int nz, const void* bc, std::initializer_list<const void*> arrays) {
   int v = requested > 0 ? requested : dflt;
-  const int vmax = 16 / (int)sizeof(TS);
+  const int vmax = 16 / esize;
   if (v > vmax) v = vmax;
   while (v & (v - 1)) --v;  // power of two
   auto aligned = [&](const void* q, size_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
   while (v > 1) {
-    const size_t a = sizeof(TS) * v;
-    if (p.nz % v == 0 && aligned(p.f0, a) && aligned(p.f1, a) && aligned(p.ghost_lo, a) && aligned(p.ghost_hi, a) &&
-        aligned(p.out_lo, a) && aligned(p.out_hi, a) && aligned(p.bc, v))
-      break;
+    bool ok = (nz % v == 0) && aligned(bc, v);
+    for (const void* q : arrays) ok = ok && aligned(q, (size_t)esize * v);
+    if (ok) break;
     v /= 2;
   }
   return v;
 }
 
 template <class L, int COLL, class TC, class TS>
-int launch_step(const StepParams<TS>& p, int x_count, int requested_v, cudaStream_t stream) {
-  // defaults chosen on B200 (profiles/): 16-byte accesses for D3Q19, 8-byte for D3Q27 (register budget)
-  constexpr int dflt = (sizeof(TS) == 8) ? 2 : ((L::Q > 19) ? 2 : 4);
-  const int v = pick_cells_per_thread<TS>(requested_v, dflt, p);
+int launch_step(const StepParams<TS>& p, int x_count, int requested_v, const void* f0, const void* f1, const void* g0, const void* g1,
+                const void* o0, const void* o1, cudaStream_t stream) {
+  // defaults chosen on B200 (profiles/): see DESIGN.md "cells per thread"
+  constexpr int dflt = (sizeof(TS) == 2) ? 2 : 1;
+  const int v = pick_cells_per_thread(requested_v, dflt, (int)sizeof(TS), p.nz, p.bc, {f0, f1, g0, g1, o0, o1});
   switch (v) {
     case 1: return launch_step_v<L, COLL, TC, TS, 1>(p, x_count, stream);
     case 2: return launch_step_v<L, COLL, TC, TS, 2>(p, x_count, stream);
@@ -328,24 +423,48 @@ int dispatch_step(const StepCall& c);
 template <class L, int COLL, class TC, class TS>
 int run_step_typed(const StepCall& c) {
   StepParams<TS> p;
-  p.f0 = static_cast<const TS*>(c.f0);
-  p.f1 = static_cast<TS*>(c.f1);
-  p.f0w = const_cast<TS*>(static_cast<const TS*>(c.f0));
+  memset(&p, 0, sizeof(p));
+  const TS* f0 = static_cast<const TS*>(c.f0);
+  TS* f1 = static_cast<TS*>(c.f1);
+  const TS* ghost_lo = static_cast<const TS*>(c.ghost_lo);
+  const TS* ghost_hi = static_cast<const TS*>(c.ghost_hi);
+  TS* out_lo = static_cast<TS*>(c.out_lo);
+  TS* out_hi = static_cast<TS*>(c.out_hi);
+  const long long plane = (long long)c.ny * c.nz;
+  const long long n = plane * c.nx;
+  if (n >= (1LL << 32)) return fail(XLBN_E_SHAPE, "more than 2^32 cells per slab (%lld): split the domain across GPUs", n);
+  static_for<L::Q>([&](auto l_) {
+    constexpr int l = decltype(l_)::value;
+    constexpr int cx = L::ck(0, l);
+    const TS* pop = f0 + (long long)l * n;
+    // element offset inside the kernel is x*plane + row + z; the tables absorb the -cx*plane shift, ghosts and wraps
+    p.pull[0][l] = pop - (long long)cx * plane;
+    p.pull[1][l] = p.pull[0][l];
+    p.pull[2][l] = p.pull[0][l];
+    if (cx == 1)  // plane x = 0 pulls plane "x = -1"
+      p.pull[1][l] = ghost_lo ? ghost_lo + (long long)L::xdir_slot(l) * plane : pop + (long long)(c.nx - 1) * plane;
+    if (cx == -1)  // plane x = nx-1 pulls plane "x = nx"; the kernel adds (nx-1)*plane
+      p.pull[2][l] = (ghost_hi ? ghost_hi + (long long)L::xdir_slot(l) * plane : pop) - (long long)(c.nx - 1) * plane;
+    p.push[l] = f1 + (long long)l * n;
+    if (cx == 1 && out_hi) p.peer_hi[l] = out_hi + (long long)L::xdir_slot(l) * plane - (long long)(c.nx - 1) * plane;
+    if (cx == -1 && out_lo) p.peer_lo[l] = out_lo + (long long)L::xdir_slot(l) * plane;
+  });
   p.bc = c.bc;
+  p.f0 = f0;
+  p.f1 = f1;
+  p.f0w = const_cast<TS*>(f0);
   p.miss = c.miss;
   p.table = c.table;
+  p.ghost_lo = ghost_lo;
+  p.ghost_hi = ghost_hi;
   p.nx = c.nx;
   p.ny = c.ny;
   p.nz = c.nz;
   p.x_begin = c.x_begin;
-  p.plane = (long long)c.ny * c.nz;
-  p.n = p.plane * c.nx;
+  p.plane = plane;
+  p.n = n;
   p.omega = c.omega;
-  p.ghost_lo = static_cast<const TS*>(c.ghost_lo);
-  p.ghost_hi = static_cast<const TS*>(c.ghost_hi);
-  p.out_lo = static_cast<TS*>(c.out_lo);
-  p.out_hi = static_cast<TS*>(c.out_hi);
-  return launch_step<L, COLL, TC, TS>(p, c.x_count, c.requested_v, c.stream);
+  return launch_step<L, COLL, TC, TS>(p, c.x_count, c.requested_v, c.f0, c.f1, c.ghost_lo, c.ghost_hi, c.out_lo, c.out_hi, c.stream);
 }
 
 #define XLBN_DEFINE_STEP_DISPATCH(LAT, COLL)                                                                      \
