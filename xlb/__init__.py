@@ -39,4 +39,7 @@ class _AliasFinder(importlib.abc.MetaPathFinder):
 
 if not any(isinstance(f, _AliasFinder) for f in sys.meta_path):
     sys.meta_path.insert(0, _AliasFinder())
+from xlb_b200.compat import install as _install_standins
+
+_install_standins()  # `warp` / `jax` names for reference scripts when the real packages are absent
 sys.modules[__name__] = xlb_b200

@@ -5,6 +5,7 @@
 struct xlbn_stepper {
   int lattice, collision, compute_dtype, store_dtype, cells_per_thread;
   bool needs_missing;
+  uint8_t kinds[256];    // host copy: bc id -> kind
   xlbn::BcEntry* table;  // device, 256 entries
   int device;
 };
@@ -78,6 +79,7 @@ int xlbn_stepper_create(const xlbn_stepper_desc* desc, xlbn_stepper** out) {
   s->cells_per_thread = cpt;
   s->needs_missing = needs_missing;
   s->table = nullptr;
+  for (int i = 0; i < 256; ++i) s->kinds[i] = (uint8_t)host[i].kind;
   cudaError_t e = cudaGetDevice(&s->device);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->table), sizeof(host));
   if (e == cudaSuccess) e = cudaMemcpy(s->table, host, sizeof(host), cudaMemcpyHostToDevice);
@@ -117,6 +119,7 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
   c.bc = bc_mask;
   c.miss = missing_bits;
   c.table = s->table;
+  c.kinds = s->kinds;
   c.omega = omega;
   c.stream = (cudaStream_t)stream;
   c.ghost_lo = c.ghost_hi = nullptr;

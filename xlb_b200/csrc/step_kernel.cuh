@@ -52,6 +52,7 @@ struct StepParams {
   TS* peer_hi[kMaxQ];  // written by plane nx-1 (c_x = +1 populations) or NULL
   TS* peer_lo[kMaxQ];  // written by plane 0    (c_x = -1 populations) or NULL
   const uint8_t* bc;
+  uint8_t kinds[256];  // bc id -> xlbn_bc_kind (constant bank; 0 for ids without a BC), so common kinds are handled inline
   // boundary-cell path only
   const TS* f0;
   TS* f1;
@@ -98,7 +99,13 @@ struct GMem<4> {
     asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
   }
-  static XLBN_DEV void st(void* p, T v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+  static XLBN_DEV void st(void* p, T v) {
+#if XLBN_ST_CS
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+    asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+  }
 };
 template <>
 struct GMem<8> {
@@ -223,14 +230,62 @@ __device__ __noinline__ void bc_cell(const StepParams<TS>& p, int id, int x, int
   XLBN_FOR(Q, l) fio[l] = f[l]; XLBN_END
 }
 
+// ---- tuning knobs (compile-time; the defaults are the values selected on B200, see profiles/ and DESIGN.md) -------
+#ifndef XLBN_MINB_OVERRIDE
+#define XLBN_MINB_OVERRIDE 0  // > 0: force __launch_bounds__(128, N) for every variant
+#endif
+#ifndef XLBN_PREFETCH
+#define XLBN_PREFETCH 0  // 1: prefetch.global.L2 the next x-plane's populations while this plane is processed
+#endif
+#ifndef XLBN_ST_CS
+#define XLBN_ST_CS 0  // 1: st.global.cs (evict-first) for the population stores
+#endif
+
 template <class L, int COLL, class TC, class TS, int V>
 struct StepTraits {
   static constexpr int kThreads = 128;
-  // register budget: V*Q population registers (x2 for fp64) + algebra temporaries and addresses
-  static constexpr int kRegs = V * L::Q * (int)(sizeof(TC) / 4) + (COLL == XLBN_KBC ? 2 * L::Q * (int)(sizeof(TC) / 4) : 24) + 24;
+  // Occupancy-first register budget (the kernel is latency-bound until ~48 warps/SM are resident, profiles/):
+  // V*Q population registers (x2 for fp64) + collision temporaries + addresses.
+  static constexpr int kW = (int)(sizeof(TC) / 4);
+  static constexpr int kRegs = V * L::Q * kW + (COLL == XLBN_KBC ? L::Q * kW + 24 : 24) + 5;
   static constexpr int kMinBlocksRaw = 65536 / (kThreads * (kRegs > 255 ? 255 : kRegs));
-  static constexpr int kMinBlocks = kMinBlocksRaw < 1 ? 1 : (kMinBlocksRaw > 12 ? 12 : kMinBlocksRaw);
+  static constexpr int kMinBlocksAuto = kMinBlocksRaw < 1 ? 1 : (kMinBlocksRaw > 12 ? 12 : kMinBlocksRaw);
+  static constexpr int kMinBlocks = XLBN_MINB_OVERRIDE > 0 ? XLBN_MINB_OVERRIDE : kMinBlocksAuto;
 };
+
+// Store V cells (fused compute -> store conversion).  The outgoing face populations of planes 0 / nx-1 ALSO go straight
+// into the neighbour GPUs' ghost planes through peer-mapped pointers.  MASKED: cells with id 255 are not written.
+template <class L, class TC, class TS, int V, int XC, bool MASKED>
+XLBN_DEV void store_cells(const StepParams<TS>& p, unsigned cell, const Pack<uint8_t, V>& ids, const TC (&f)[V][L::Q]) {
+  if constexpr (!MASKED) {
+    XLBN_FOR(L::Q, l)
+      Pack<TS, V> a;
+#pragma unroll
+      for (int v = 0; v < V; ++v) a.v[v] = Cvt<TC, TS>::down(f[v][l]);
+      gstore<TS, V>(p.push[l] + cell, a);
+      if constexpr (L::ck(0, l) == 1 && (XC & 2)) {
+        if (p.peer_hi[l]) gstore<TS, V>(p.peer_hi[l] + cell, a);
+      } else if constexpr (L::ck(0, l) == -1 && (XC & 1)) {
+        if (p.peer_lo[l]) gstore<TS, V>(p.peer_lo[l] + cell, a);
+      }
+    XLBN_END
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (ids.v[v] == 255) continue;
+      XLBN_FOR(L::Q, l)
+        Pack<TS, 1> a;
+        a.v[0] = Cvt<TC, TS>::down(f[v][l]);
+        gstore<TS, 1>(p.push[l] + (cell + v), a);
+        if constexpr (L::ck(0, l) == 1 && (XC & 2)) {
+          if (p.peer_hi[l]) gstore<TS, 1>(p.peer_hi[l] + (cell + v), a);
+        } else if constexpr (L::ck(0, l) == -1 && (XC & 1)) {
+          if (p.peer_lo[l]) gstore<TS, 1>(p.peer_lo[l] + (cell + v), a);
+        }
+      XLBN_END
+    }
+  }
+}
 
 // XC = x-plane class of this block: 0 interior, 1 plane 0, 2 plane nx-1, 3 both (nx == 1)
 template <class L, int COLL, class TC, class TS, int V, int XC>
@@ -265,10 +320,16 @@ XLBN_DEV void step_body(const StepParams<TS>& p, const int x, const int y, const
     const unsigned row = (cy == 1 ? row_m : (cy == -1 ? row_p : row_c));
     if constexpr (cz == 0) {
       const Pack<TS, V> a = gload<TS, V>(base + (row + (unsigned)z0));
+#if XLBN_PREFETCH
+      if constexpr (XC == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (row + (unsigned)z0) + p.plane));
+#endif
 #pragma unroll
       for (int v = 0; v < V; ++v) f[v][l] = Cvt<TC, TS>::up(a.v[v]);
     } else if constexpr (V == 1) {
       const Pack<TS, 1> a = gload<TS, 1>(base + (row + (cz == 1 ? z_lo : z_hi)));
+#if XLBN_PREFETCH
+      if constexpr (XC == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (row + (cz == 1 ? z_lo : z_hi)) + p.plane));
+#endif
       f[0][l] = Cvt<TC, TS>::up(a.v[0]);
     } else if constexpr (cz == 1) {  // out[z] = in[z - 1]
       const Pack<TS, V> a = gload<TS, V>(base + (row + (unsigned)z0));
@@ -287,52 +348,44 @@ XLBN_DEV void step_body(const StepParams<TS>& p, const int x, const int y, const
 
   const TC omega = (TC)p.omega;
   if (!any_bc) {
+    // straight-line path: no boundary cell among this thread's V cells (ends here, so that its register allocation is
+    // independent of the boundary code below)
 #pragma unroll
     for (int v = 0; v < V; ++v) collide_cell<L, COLL, TC>(f[v], omega);
-  } else {
+    store_cells<L, TC, TS, V, XC, false>(p, cell, ids, f);
+    return;
+  }
+  // Threads with boundary cells.  The two kinds that make up closed-box walls and lids are handled in registers:
+  //   FullwayBounceBack: out[l] = f_post_stream[opp[l]], no collision needed (bc_fullway_bounce_back.py:60-72)
+  //   EquilibriumBC    : f = feq(rho_bc, u_bc), then the ordinary collision (bc_equilibrium.py:76-86)
+  // every other kind goes through the out-of-line boundary-cell routine.
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const int id = ids.v[v];
-      if (id == 0) {
-        collide_cell<L, COLL, TC>(f[v], omega);
-      } else if (id != 255) {
-        TC tmp[Q];
-        XLBN_FOR(Q, l) tmp[l] = f[v][l]; XLBN_END
-        bc_cell<L, COLL, TC, TS>(p, id, x, y, z0 + v, tmp);
-        XLBN_FOR(Q, l) f[v][l] = tmp[l]; XLBN_END
-      }
+  for (int v = 0; v < V; ++v) {
+    const int id = ids.v[v];
+    if (id == 255) continue;
+    int kind = id ? (int)p.kinds[id] : 0;
+    if (kind == XLBN_BC_EQUILIBRIUM) {
+      const BcEntry* e = p.table + id;
+      TC u[L::D];
+      XLBN_FOR(L::D, d) u[d] = (TC)e->u[d]; XLBN_END
+      equilibrium<L, TC>((TC)e->rho, u, f[v]);
+      kind = XLBN_BC_NONE;
+    }
+    if (kind == XLBN_BC_NONE) {
+      collide_cell<L, COLL, TC>(f[v], omega);
+    } else if (kind == XLBN_BC_FULLWAY_BOUNCE_BACK) {
+      TC t[Q];
+      XLBN_FOR(Q, l) t[l] = f[v][L::opp(l)]; XLBN_END
+      XLBN_FOR(Q, l) f[v][l] = t[l]; XLBN_END
+    } else {
+      TC tmp[Q];
+      XLBN_FOR(Q, l) tmp[l] = f[v][l]; XLBN_END
+      bc_cell<L, COLL, TC, TS>(p, id, x, y, z0 + v, tmp);
+      XLBN_FOR(Q, l) f[v][l] = tmp[l]; XLBN_END
     }
   }
-
-  // store (fused compute -> store conversion); outgoing face populations also go to the neighbour GPUs' ghost planes
-  if (!any_solid) {
-    XLBN_FOR(Q, l)
-      Pack<TS, V> a;
-#pragma unroll
-      for (int v = 0; v < V; ++v) a.v[v] = Cvt<TC, TS>::down(f[v][l]);
-      gstore<TS, V>(p.push[l] + cell, a);
-      if constexpr (L::ck(0, l) == 1 && (XC & 2)) {
-        if (p.peer_hi[l]) gstore<TS, V>(p.peer_hi[l] + cell, a);
-      } else if constexpr (L::ck(0, l) == -1 && (XC & 1)) {
-        if (p.peer_lo[l]) gstore<TS, V>(p.peer_lo[l] + cell, a);
-      }
-    XLBN_END
-  } else {
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      if (ids.v[v] == 255) continue;
-      XLBN_FOR(Q, l)
-        Pack<TS, 1> a;
-        a.v[0] = Cvt<TC, TS>::down(f[v][l]);
-        gstore<TS, 1>(p.push[l] + (cell + v), a);
-        if constexpr (L::ck(0, l) == 1 && (XC & 2)) {
-          if (p.peer_hi[l]) gstore<TS, 1>(p.peer_hi[l] + (cell + v), a);
-        } else if constexpr (L::ck(0, l) == -1 && (XC & 1)) {
-          if (p.peer_lo[l]) gstore<TS, 1>(p.peer_lo[l] + (cell + v), a);
-        }
-      XLBN_END
-    }
-  }
+  if (any_solid) store_cells<L, TC, TS, V, XC, true>(p, cell, ids, f);
+  else store_cells<L, TC, TS, V, XC, false>(p, cell, ids, f);
 }
 
 template <class L, int COLL, class TC, class TS, int V>
@@ -408,6 +461,7 @@ struct StepCall {
   const uint8_t* bc;
   const uint32_t* miss;
   const BcEntry* table;
+  const uint8_t* kinds;  // host, 256 entries
   int nx, ny, nz, x_begin, x_count;
   double omega;
   const void* ghost_lo;
@@ -450,6 +504,7 @@ int run_step_typed(const StepCall& c) {
     if (cx == -1 && out_lo) p.peer_lo[l] = out_lo + (long long)L::xdir_slot(l) * plane;
   });
   p.bc = c.bc;
+  memcpy(p.kinds, c.kinds, 256);
   p.f0 = f0;
   p.f1 = f1;
   p.f0w = const_cast<TS*>(f0);

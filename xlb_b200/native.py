@@ -15,7 +15,7 @@ from functools import lru_cache
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxlb_b200.so")
+LIB_PATH = os.environ.get("XLB_B200_LIB") or os.path.join(_HERE, "libxlb_b200.so")  # env override: tuning builds only
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 # enums of include/xlb_b200.h
