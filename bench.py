@@ -40,7 +40,7 @@ def parse():
     p.add_argument("--lattice", default="D3Q19", choices=list(Q))
     p.add_argument("--collision", default="BGK", choices=["BGK", "KBC"])
     p.add_argument("--policy", default="FP32FP32", choices=list(STORE_BYTES))
-    p.add_argument("--config", default="cavity", choices=["cavity", "periodic"])
+    p.add_argument("--config", default="cavity", choices=["cavity", "periodic", "sphere", "tunnel"])
     p.add_argument("--cells-per-thread", type=int, default=0)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -126,8 +126,52 @@ def build_case(args, shape):
         walls = [box["bottom"][i] + box["left"][i] + box["right"][i] + box["front"][i] + box["back"][i] for i in range(3)]
         walls = np.unique(np.array(walls), axis=-1).tolist()
         bcs = [EquilibriumBC(rho=1.0, u=(0.02, 0.0, 0.0), indices=lid), FullwayBounceBackBC(indices=walls)]
+    elif args.config in ("sphere", "tunnel"):
+        bcs = obstacle_bcs(args.config, grid, shape)
     stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=bcs, collision_type=args.collision, cells_per_thread=args.cells_per_thread)
     return grid, stepper
+
+
+def obstacle_bcs(kind, grid, shape):
+    """C3: flow past a sphere (examples/cfd/flow_past_sphere_3d.py:41-109 geometry: Fullway walls, Regularized velocity
+    inlet with a Poiseuille profile, ExtrapolationOutflow outlet, Halfway sphere by index inequality).
+    C4: the same tunnel with a synthetic voxelised bluff body (seeded union of boxes + an ellipsoid, seed 0) and a uniform
+    inlet (examples/cfd/windtunnel_3d.py:92-96 boundary set)."""
+    from xlb_b200.operator.boundary_condition import ExtrapolationOutflowBC, FullwayBounceBackBC, HalfwayBounceBackBC, RegularizedBC
+
+    nx, ny, nz = shape
+    box, bne = grid.bounding_box_indices(), grid.bounding_box_indices(remove_edges=True)
+    walls = [box["bottom"][i] + box["top"][i] + box["front"][i] + box["back"][i] for i in range(3)]
+    walls = np.unique(np.array(walls), axis=-1).tolist()
+    if kind == "sphere":
+        r = ny // 12
+        cx, cy, cz = nx // 6, ny // 2, nz // 2
+        xs = np.arange(cx - r, cx + r + 1)
+        X, Y, Z = np.meshgrid(xs, np.arange(cy - r, cy + r + 1), np.arange(cz - r, cz + r + 1), indexing="ij")
+        m = (X - cx) ** 2 + (Y - cy) ** 2 + (Z - cz) ** 2 < r**2
+        body = [X[m].tolist(), Y[m].tolist(), Z[m].tolist()]
+        Hy, Hz = float(ny - 1), float(nz - 1)
+
+        def profile(index):
+            yc, zc = index[1] - Hy / 2.0, index[2] - Hz / 2.0
+            return [0.04 * np.maximum(0.0, 1.0 - ((2.0 * yc / Hy) ** 2.0 + (2.0 * zc / Hz) ** 2.0))]
+
+        inlet = RegularizedBC("velocity", profile=profile, indices=bne["left"])
+    else:
+        rng = np.random.default_rng(0)
+        solid = np.zeros((nx // 4, ny // 2, nz // 3), dtype=bool)  # body region x in [nx/4, nx/2)
+        sx, sy, sz = solid.shape
+        for _ in range(6):
+            lo = [rng.integers(0, s // 2) for s in solid.shape]
+            hi = [l + rng.integers(s // 4, s // 2) for l, s in zip(lo, solid.shape)]
+            solid[lo[0] : hi[0], lo[1] : hi[1], lo[2] : hi[2]] = True
+        X, Y, Z = np.meshgrid(np.arange(sx), np.arange(sy), np.arange(sz), indexing="ij")
+        solid |= ((X - sx / 2) / (sx / 2.2)) ** 2 + ((Y - sy / 2) / (sy / 2.5)) ** 2 + ((Z - sz / 3) / (sz / 3.0)) ** 2 < 1.0
+        solid[:, :, :2] = False
+        ix, iy, iz = np.nonzero(solid)
+        body = [(ix + nx // 4).tolist(), (iy + ny // 4).tolist(), (iz + 2).tolist()]
+        inlet = RegularizedBC("velocity", prescribed_value=(0.02, 0.0, 0.0), indices=bne["left"])
+    return [FullwayBounceBackBC(indices=walls), inlet, ExtrapolationOutflowBC(indices=bne["right"]), HalfwayBounceBackBC(indices=body)]
 
 
 def run_native(args):
@@ -149,11 +193,13 @@ def run_native(args):
 
     n = args.n
     shape = (n * world, n, n)  # weak scaling: n^3 per GPU, x-slabs
+    if args.config in ("sphere", "tunnel"):  # BASELINE C3: 1024x512x512 (= 2n x n x n); C4: 1152x512x512 over 8 GPUs (= 9n/4 x n x n)
+        shape = (2 * n, n, n) if args.config == "sphere" else (9 * n // 4 // world * world, n, n)
     grid, stepper = build_case(args, shape)
     f_0, f_1, bc_mask, missing_mask = stepper.prepare_fields()
-    omega = 1.0
-    cells_local = n * n * n
-    cells_total = cells_local * world
+    omega = 1.0 if args.config in ("cavity", "periodic") else 1.6
+    cells_total = shape[0] * shape[1] * shape[2]
+    cells_local = cells_total // world
 
     def loop(k, t0):
         nonlocal f_0, f_1
@@ -216,13 +262,15 @@ def run_native(args):
     if rank == 0:
         line = {
             "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak" if args.config in ("cavity", "periodic") else "strong", "vs_baseline": None,
             "dtype": {"FP32FP32": "f32", "FP32FP16": "f32 compute / f16 store", "FP64FP32": "f64 compute / f32 store", "FP64FP64": "f64", "FP64FP16": "f64 compute / f16 store"}[args.policy],
             "data": "synthetic",
             "config": {
                 "workload": f"{args.config} {args.lattice} {args.collision} {n}^3 per GPU {args.policy} (global {shape[0]}x{shape[1]}x{shape[2]}); "
-                            + ("lid-driven cavity of examples/performance/mlups_3d.py" if args.config == "cavity" else "fully periodic box"),
-                "omega": omega, "l2": "inputs (2 x %.1f GB) larger than L2, no flush" % (Q[args.lattice] * STORE_BYTES[args.policy] * cells_local / 1e9),
+                            + {"cavity": "lid-driven cavity of examples/performance/mlups_3d.py", "periodic": "fully periodic box",
+                               "sphere": "flow past a sphere (examples/cfd/flow_past_sphere_3d.py geometry)",
+                               "tunnel": "synthetic voxelised bluff body in a wind tunnel (windtunnel_3d.py boundary set)"}[args.config],
+                "omega": omega, "l2": "inputs (2 x %.1f GB per GPU) larger than L2, no flush" % (Q[args.lattice] * STORE_BYTES[args.policy] * cells_local / 1e9),
                 "parallelism": "1 GPU" if world == 1 else f"x-slab x{world}, halo fused into the face-plane kernels (peer stores over NVLink)",
                 "cells_per_thread": args.cells_per_thread or "default",
             },

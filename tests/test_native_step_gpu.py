@@ -26,11 +26,15 @@ def test_step_matches_reference_vectors(name, backend):
     assert rel_err(f, g["f_final"]) <= RTOL[g["policy"]], f"{name}: rel err {rel_err(f, g['f_final']):.3e}"
 
 
-@pytest.mark.parametrize("v", [1, 2, 4, 8])
+@pytest.mark.parametrize("v", [1, 2, 4, 8, 102, 104])  # 10x = packed fp32x2 pair path (falls back to scalar for fp64)
 @pytest.mark.parametrize("name", ["cavity_d3q19_bgk_fp32", "cavity_d3q19_bgk_fp32fp16", "sphere_d3q27_kbc_fp32", "sphere_d3q27_bgk_regpressure_fp64", "cavity_d2q9_kbc_fp32"])
 def test_every_cells_per_thread_variant(name, v):
     """All vector widths of the kernel compute the same step (the library falls back when v does not divide nz)."""
     g = load_golden(name)
+    if v >= 100 and g["policy"].startswith("FP64"):
+        with pytest.raises(Exception, match="packed pair path"):
+            native_run(g, cells_per_thread=v)
+        return
     f, _, _ = native_run(g, cells_per_thread=v)
     assert rel_err(f, g["f_final"]) <= RTOL[g["policy"]]
 
@@ -112,3 +116,41 @@ def test_c1_cavity_1000_steps_against_c_oracle(n):
     rho_n, u_n = O.macroscopic(f, lat)
     assert rel_err(rho_n, rho_r) <= 1e-5
     assert np.abs(u_n - u_r).max() <= 1e-5 * 0.02
+
+
+@pytest.mark.parametrize("v", [0, 1, 102])
+def test_c3_sphere_d3q27_kbc_256x64x64_against_c_oracle(v):
+    """BASELINE config C3 at the reference example's own size (examples/cfd/flow_past_sphere_3d.py:22: 256x64x64):
+    D3Q27 KBC omega 1.6, Fullway walls, Regularized Poiseuille inlet, ExtrapolationOutflow outlet, Halfway sphere.
+    300 steps against the C oracle; masks bit-exact, populations within 1e-5 relative."""
+    from oracle import lbm_c
+    from oracle import lbm_numpy as O
+
+    if not lbm_c.available():
+        pytest.skip("oracle/liblbm_ref.so not built")
+    shape, lat = (256, 64, 64), O.Lattice("D3Q27")
+    box, bne = O.bounding_box_indices(shape), O.bounding_box_indices(shape, remove_edges=True)
+    walls = np.unique(np.concatenate([box[k] for k in ("bottom", "top", "front", "back")], axis=1), axis=-1)
+    X, Y, Z = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+    sph = np.array(np.where((X - shape[0] // 6) ** 2 + (Y - shape[1] // 2) ** 2 + (Z - shape[2] // 2) ** 2 < (shape[1] // 12) ** 2))
+    Hy, Hz = float(shape[1] - 1), float(shape[2] - 1)
+    yy, zz = np.meshgrid(np.arange(shape[1]), np.arange(shape[2]), indexing="ij")
+    ux = (0.04 * np.maximum(0.0, 1.0 - ((2.0 * (yy - Hy / 2.0) / Hy) ** 2.0 + (2.0 * (zz - Hz / 2.0) / Hz) ** 2.0))).astype(np.float32)
+    pv = np.stack([ux, np.zeros_like(ux), np.zeros_like(ux)])
+    g = load_golden("sphere_d3q27_kbc_fp32")
+    g.update(shape=shape, steps=300, omega=1.6, f_init=O.initialize_eq(shape, lat))
+    g["bcs"] = [
+        dict(kind="fullway", id=1, indices=walls),
+        dict(kind="regularized", id=2, indices=bne["left"], bc_type="velocity", prescribed=pv),
+        dict(kind="outflow", id=3, indices=bne["right"]),
+        dict(kind="halfway", id=4, indices=sph),
+    ]
+    from common import oracle_bcs
+
+    bcs = oracle_bcs(g)
+    bc_mask, missing = O.build_masks(bcs, shape, lat, flavor="warp")
+    ref = lbm_c.run(g["f_init"], bc_mask, missing, bcs, 1.6, lat, 300, "FP32FP32", "KBC")
+    f, bm, mm = native_run(g, cells_per_thread=v)
+    assert np.array_equal(bm, bc_mask) and np.array_equal(mm, missing)
+    assert np.isfinite(f).all()
+    assert rel_err(f, ref) <= 1e-5, rel_err(f, ref)

@@ -107,10 +107,17 @@ struct IC {
   __host__ __device__ constexpr operator int() const { return I; }
 };
 template <int N, int I = 0, class F>
-__host__ __device__ __forceinline__ void static_for(F&& fn) {
+__device__ __forceinline__ void static_for(F&& fn) {
   if constexpr (I < N) {
     fn(IC<I>{});
     static_for<N, I + 1>(fn);
+  }
+}
+template <int N, int I = 0, class F>
+inline void static_for_host(F&& fn) {
+  if constexpr (I < N) {
+    fn(IC<I>{});
+    static_for_host<N, I + 1>(fn);
   }
 }
 

@@ -13,7 +13,8 @@ namespace xlbn {
 
 // rho = sum_l f_l ; u_d = (sum_{c=+1} f - sum_{c=-1} f) / rho
 // (reference: zero_moment.py:32-37, first_moment.py:26-38, macroscopic.py:43-47)
-template <class L, class TC>
+// FAST: u = (sum c f) * (1/rho) instead of three divisions (<= 1 ulp difference); used where the kernel is issue-bound
+template <class L, class TC, bool FAST = false>
 XLBN_DEV void macroscopic(const TC (&f)[L::Q], TC& rho, TC (&u)[L::D]) {
   rho = TC(0);
   XLBN_FOR(L::Q, l) rho += f[l]; XLBN_END
@@ -24,15 +25,20 @@ XLBN_DEV void macroscopic(const TC (&f)[L::Q], TC& rho, TC (&u)[L::D]) {
       else if constexpr (L::c(d, l) == -1) u[d] -= f[l];
     XLBN_END
   XLBN_END
-  XLBN_FOR(L::D, d) u[d] /= rho; XLBN_END
+  if constexpr (FAST) {
+    const TC inv = rcp_(rho);
+    XLBN_FOR(L::D, d) u[d] = u[d] * inv; XLBN_END
+  } else {
+    XLBN_FOR(L::D, d) u[d] /= rho; XLBN_END
+  }
 }
 
 // feq_l = rho w_l (1 + cu (1 + 0.5 cu) - usqr), cu = 3 c_l.u, usqr = 1.5 u.u
 // (reference: quadratic_equilibrium.py:35-60)
 template <class L, class TC>
 XLBN_DEV void equilibrium(TC rho, const TC (&u)[L::D], TC (&feq)[L::Q]) {
-  TC uu = TC(0);
-  XLBN_FOR(L::D, d) uu += u[d] * u[d]; XLBN_END
+  TC uu = u[0] * u[0];
+  XLBN_FOR(L::D - 1, d) uu = fma_(u[d + 1], u[d + 1], uu); XLBN_END
   const TC usqr = TC(1.5) * uu;
   XLBN_FOR(L::Q, l)
     TC cu = TC(0);
@@ -41,7 +47,8 @@ XLBN_DEV void equilibrium(TC rho, const TC (&u)[L::D], TC (&feq)[L::Q]) {
       else if constexpr (L::c(d, l) == -1) cu -= u[d];
     XLBN_END
     cu *= TC(3.0);
-    feq[l] = rho * TC(L::w(l)) * (TC(1.0) + cu * (TC(1.0) + TC(0.5) * cu) - usqr);
+    // 1 + cu (1 + cu/2) - usqr with the two contractions written out (same result for every compute type)
+    feq[l] = rho * TC(L::w(l)) * (fma_(cu, fma_(TC(0.5), cu, TC(1.0)), TC(1.0)) - usqr);
   XLBN_END
 }
 
@@ -62,12 +69,12 @@ template <class L, class TC>
 XLBN_DEV void collide_bgk(const TC (&f)[L::Q], const TC (&feq)[L::Q], TC omega, TC (&out)[L::Q]) {
   XLBN_FOR(L::Q, l)
     const TC fneq = f[l] - feq[l];
-    out[l] = f[l] - omega * fneq;
+    out[l] = fma_(-omega, fneq, f[l]);
   XLBN_END
 }
 
 // KBC shear part of fneq (reference: kbc.py:188-250).  s_l for the D3Q27 / D2Q9 lattices.
-template <class L, class TC>
+template <class L, class TC, bool FAST = false>
 XLBN_DEV void kbc_shear(const TC (&fneq)[L::Q], TC (&s)[L::Q]) {
   TC pi[L::NT];
   second_moment<L, TC>(fneq, pi);
@@ -75,11 +82,17 @@ XLBN_DEV void kbc_shear(const TC (&fneq)[L::Q], TC (&s)[L::Q]) {
   if constexpr (L::ID == XLBN_D3Q27) {
     const TC nxz = pi[0] - pi[5];
     const TC nyz = pi[3] - pi[5];
-    s[9] = (TC(2.0) * nxz - nyz) / TC(6.0);
+    if constexpr (FAST) {  // x / 6 as x * (1/6): one rounding of the constant instead of a division
+      s[9] = (TC(2.0) * nxz - nyz) * TC(1.0 / 6.0);
+      s[3] = (-nxz + TC(2.0) * nyz) * TC(1.0 / 6.0);
+      s[1] = (-nxz - nyz) * TC(1.0 / 6.0);
+    } else {
+      s[9] = (TC(2.0) * nxz - nyz) / TC(6.0);
+      s[3] = (-nxz + TC(2.0) * nyz) / TC(6.0);
+      s[1] = (-nxz - nyz) / TC(6.0);
+    }
     s[18] = s[9];
-    s[3] = (-nxz + TC(2.0) * nyz) / TC(6.0);
     s[6] = s[3];
-    s[1] = (-nxz - nyz) / TC(6.0);
     s[2] = s[1];
     s[12] = pi[1] / TC(4.0);
     s[24] = s[12];
@@ -107,11 +120,12 @@ XLBN_DEV void kbc_shear(const TC (&fneq)[L::Q], TC (&s)[L::Q]) {
 }
 
 // KBC (reference: kbc.py:268-296): entropic stabiliser gamma from the scalar products <dh|ds>, <dh|dh> weighted by 1/feq.
-template <class L, class TC>
+// FAST: the 27 divisions dh/feq (they only feed the scalar stabiliser gamma) become dh * rcp(feq)
+template <class L, class TC, bool FAST = false>
 XLBN_DEV void collide_kbc(const TC (&f)[L::Q], const TC (&feq)[L::Q], TC rho, TC omega, TC (&out)[L::Q]) {
   TC fneq[L::Q], ds[L::Q];
   XLBN_FOR(L::Q, l) fneq[l] = f[l] - feq[l]; XLBN_END
-  kbc_shear<L, TC>(fneq, ds);
+  kbc_shear<L, TC, FAST>(fneq, ds);
   XLBN_FOR(L::Q, l)
     if constexpr (L::D == 3) ds[l] = ds[l] * rho;
     else ds[l] = ds[l] * rho / TC(4.0);
@@ -121,25 +135,29 @@ XLBN_DEV void collide_kbc(const TC (&f)[L::Q], const TC (&feq)[L::Q], TC rho, TC
   TC sp1 = TC(0), sp2 = TC(0);
   XLBN_FOR(L::Q, l)
     const TC dh = fneq[l] - ds[l];
-    const TC temp = dh / feq[l];
-    sp1 += temp * ds[l];
-    sp2 += temp * dh;
+    TC temp;
+    if constexpr (FAST) temp = dh * rcp_approx_(feq[l]);
+    else temp = dh / feq[l];
+    sp1 = fma_(temp, ds[l], sp1);
+    sp2 = fma_(temp, dh, sp2);
   XLBN_END
   const TC gamma = inv_beta - (TC(2.0) - inv_beta) * sp1 / (TC(1e-32) + sp2);
   XLBN_FOR(L::Q, l)
     const TC dh = fneq[l] - ds[l];
-    out[l] = f[l] - beta * (TC(2.0) * ds[l] + gamma * dh);
+    out[l] = fma_(-beta, fma_(gamma, dh, TC(2.0) * ds[l]), f[l]);
   XLBN_END
 }
 
 // macroscopic -> equilibrium -> collision on one cell, in place (reference: nse_stepper.py:369-371).
-template <class L, int COLL, class TC>
+// FAST selects reciprocal-based divisions (see macroscopic / collide_kbc); the fused kernel uses it where it is
+// issue-bound (KBC, and the packed pair path), never for fp64.
+template <class L, int COLL, class TC, bool FAST = false>
 XLBN_DEV void collide_cell(TC (&f)[L::Q], TC omega) {
   TC rho, u[L::D], feq[L::Q], out[L::Q];
-  macroscopic<L, TC>(f, rho, u);
+  macroscopic<L, TC, FAST>(f, rho, u);
   equilibrium<L, TC>(rho, u, feq);
   if constexpr (COLL == XLBN_BGK) collide_bgk<L, TC>(f, feq, omega, out);
-  else collide_kbc<L, TC>(f, feq, rho, omega, out);
+  else collide_kbc<L, TC, FAST>(f, feq, rho, omega, out);
   XLBN_FOR(L::Q, l) f[l] = out[l]; XLBN_END
 }
 

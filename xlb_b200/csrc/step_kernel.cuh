@@ -151,6 +151,10 @@ XLBN_DEV void gstore(T* p, const Pack<T, V>& x) {
   G::st(p, u.raw);
 }
 
+// FAST (reciprocal-based) divisions where the kernel is issue-bound: single-precision KBC.  fp64 and BGK keep IEEE division.
+template <int COLL, class TC>
+constexpr bool kFast = (COLL == XLBN_KBC) && (sizeof(TC) == 4);
+
 // f0[l] at an arbitrary (possibly out-of-range) kernel-coordinate cell: periodic in y/z; x through ghost or wrap.
 template <class L, class TC, class TS>
 __device__ TC load_f0_any(const StepParams<TS>& p, int l, int ck0, int slot, int x, int y, int z) {
@@ -220,12 +224,12 @@ __device__ __noinline__ void bc_cell(const StepParams<TS>& p, int id, int x, int
         aux[l] = (TC(1.0) - cs) * f[l] + cs * fn;
       }
     XLBN_END
-    collide_cell<L, COLL, TC>(f, omega);
+    collide_cell<L, COLL, TC, kFast<COLL, TC>>(f, omega);
     XLBN_FOR(Q, l)
       if ((miss >> l) & 1u) f[L::opp(l)] = aux[l];
     XLBN_END
   } else {
-    collide_cell<L, COLL, TC>(f, omega);
+    collide_cell<L, COLL, TC, kFast<COLL, TC>>(f, omega);
   }
   XLBN_FOR(Q, l) fio[l] = f[l]; XLBN_END
 }
@@ -241,13 +245,14 @@ __device__ __noinline__ void bc_cell(const StepParams<TS>& p, int id, int x, int
 #define XLBN_ST_CS 0  // 1: st.global.cs (evict-first) for the population stores
 #endif
 
-template <class L, int COLL, class TC, class TS, int V>
+template <class L, int COLL, class TC, class TS, int V, bool PK = false>
 struct StepTraits {
   static constexpr int kThreads = 128;
   // Occupancy-first register budget (the kernel is latency-bound until ~48 warps/SM are resident, profiles/):
   // V*Q population registers (x2 for fp64) + collision temporaries + addresses.
   static constexpr int kW = (int)(sizeof(TC) / 4);
-  static constexpr int kRegs = V * L::Q * kW + (COLL == XLBN_KBC ? L::Q * kW + 24 : 24) + 5;
+  static constexpr int kRegs = PK ? V * L::Q + (COLL == XLBN_KBC ? 4 : 2) * L::Q + 29  // pair temporaries take two registers each
+                                  : V * L::Q * kW + (COLL == XLBN_KBC ? L::Q * kW + 24 : 24) + 5;
   static constexpr int kMinBlocksRaw = 65536 / (kThreads * (kRegs > 255 ? 255 : kRegs));
   static constexpr int kMinBlocksAuto = kMinBlocksRaw < 1 ? 1 : (kMinBlocksRaw > 12 ? 12 : kMinBlocksRaw);
   static constexpr int kMinBlocks = XLBN_MINB_OVERRIDE > 0 ? XLBN_MINB_OVERRIDE : kMinBlocksAuto;
@@ -285,6 +290,44 @@ XLBN_DEV void store_cells(const StepParams<TS>& p, unsigned cell, const Pack<uin
       XLBN_END
     }
   }
+}
+
+template <class L, int COLL, class TC, class TS, int V, int XC>
+XLBN_DEV void bc_tail(const StepParams<TS>& p, const Pack<uint8_t, V>& ids, const int x, const int y, const int z0, const unsigned cell,
+                      const bool any_solid, TC (&f)[V][L::Q]) {
+  constexpr int Q = L::Q;
+  const TC omega = (TC)p.omega;
+  // Threads with boundary cells.  The two kinds that make up closed-box walls and lids are handled in registers:
+  //   FullwayBounceBack: out[l] = f_post_stream[opp[l]], no collision needed (bc_fullway_bounce_back.py:60-72)
+  //   EquilibriumBC    : f = feq(rho_bc, u_bc), then the ordinary collision (bc_equilibrium.py:76-86)
+  // every other kind goes through the out-of-line boundary-cell routine.
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int id = ids.v[v];
+    if (id == 255) continue;
+    int kind = id ? (int)p.kinds[id] : 0;
+    if (kind == XLBN_BC_EQUILIBRIUM) {
+      const BcEntry* e = p.table + id;
+      TC u[L::D];
+      XLBN_FOR(L::D, d) u[d] = (TC)e->u[d]; XLBN_END
+      equilibrium<L, TC>((TC)e->rho, u, f[v]);
+      kind = XLBN_BC_NONE;
+    }
+    if (kind == XLBN_BC_NONE) {
+      collide_cell<L, COLL, TC, kFast<COLL, TC>>(f[v], omega);
+    } else if (kind == XLBN_BC_FULLWAY_BOUNCE_BACK) {
+      TC t[Q];
+      XLBN_FOR(Q, l) t[l] = f[v][L::opp(l)]; XLBN_END
+      XLBN_FOR(Q, l) f[v][l] = t[l]; XLBN_END
+    } else {
+      TC tmp[Q];
+      XLBN_FOR(Q, l) tmp[l] = f[v][l]; XLBN_END
+      bc_cell<L, COLL, TC, TS>(p, id, x, y, z0 + v, tmp);
+      XLBN_FOR(Q, l) f[v][l] = tmp[l]; XLBN_END
+    }
+  }
+  if (any_solid) store_cells<L, TC, TS, V, XC, true>(p, cell, ids, f);
+  else store_cells<L, TC, TS, V, XC, false>(p, cell, ids, f);
 }
 
 // XC = x-plane class of this block: 0 interior, 1 plane 0, 2 plane nx-1, 3 both (nx == 1)
@@ -349,47 +392,110 @@ XLBN_DEV void step_body(const StepParams<TS>& p, const int x, const int y, const
   const TC omega = (TC)p.omega;
   if (!any_bc) {
     // straight-line path: no boundary cell among this thread's V cells (ends here, so that its register allocation is
-    // independent of the boundary code below)
+    // independent of the boundary code)
 #pragma unroll
-    for (int v = 0; v < V; ++v) collide_cell<L, COLL, TC>(f[v], omega);
+    for (int v = 0; v < V; ++v) collide_cell<L, COLL, TC, kFast<COLL, TC>>(f[v], omega);
     store_cells<L, TC, TS, V, XC, false>(p, cell, ids, f);
     return;
   }
-  // Threads with boundary cells.  The two kinds that make up closed-box walls and lids are handled in registers:
-  //   FullwayBounceBack: out[l] = f_post_stream[opp[l]], no collision needed (bc_fullway_bounce_back.py:60-72)
-  //   EquilibriumBC    : f = feq(rho_bc, u_bc), then the ordinary collision (bc_equilibrium.py:76-86)
-  // every other kind goes through the out-of-line boundary-cell routine.
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    const int id = ids.v[v];
-    if (id == 255) continue;
-    int kind = id ? (int)p.kinds[id] : 0;
-    if (kind == XLBN_BC_EQUILIBRIUM) {
-      const BcEntry* e = p.table + id;
-      TC u[L::D];
-      XLBN_FOR(L::D, d) u[d] = (TC)e->u[d]; XLBN_END
-      equilibrium<L, TC>((TC)e->rho, u, f[v]);
-      kind = XLBN_BC_NONE;
-    }
-    if (kind == XLBN_BC_NONE) {
-      collide_cell<L, COLL, TC>(f[v], omega);
-    } else if (kind == XLBN_BC_FULLWAY_BOUNCE_BACK) {
-      TC t[Q];
-      XLBN_FOR(Q, l) t[l] = f[v][L::opp(l)]; XLBN_END
-      XLBN_FOR(Q, l) f[v][l] = t[l]; XLBN_END
-    } else {
-      TC tmp[Q];
-      XLBN_FOR(Q, l) tmp[l] = f[v][l]; XLBN_END
-      bc_cell<L, COLL, TC, TS>(p, id, x, y, z0 + v, tmp);
-      XLBN_FOR(Q, l) f[v][l] = tmp[l]; XLBN_END
-    }
-  }
-  if (any_solid) store_cells<L, TC, TS, V, XC, true>(p, cell, ids, f);
-  else store_cells<L, TC, TS, V, XC, false>(p, cell, ids, f);
+  bc_tail<L, COLL, TC, TS, V, XC>(p, ids, x, y, z0, cell, any_solid, f);
 }
 
-template <class L, int COLL, class TC, class TS, int V>
-__global__ void __launch_bounds__(StepTraits<L, COLL, TC, TS, V>::kThreads, StepTraits<L, COLL, TC, TS, V>::kMinBlocks)
+// ---- packed pair path: two neighbouring cells per fp32x2 register pair (FADD2 / FMUL2 / FFMA2) ---------------------
+template <class TS>
+XLBN_DEV f32x2 pair_up(TS lo, TS hi);
+template <>
+XLBN_DEV f32x2 pair_up<float>(float lo, float hi) { return f32x2(lo, hi); }
+template <>
+XLBN_DEV f32x2 pair_up<__half>(__half lo, __half hi) { return f32x2(__half22float2(__halves2half2(lo, hi))); }
+template <class TS>
+XLBN_DEV void pair_down(f32x2 v, TS& lo, TS& hi);
+template <>
+XLBN_DEV void pair_down<float>(f32x2 v, float& lo, float& hi) { lo = v.v.x; hi = v.v.y; }
+template <>
+XLBN_DEV void pair_down<__half>(f32x2 v, __half& lo, __half& hi) {
+  const __half2 h = __float22half2_rn(v.v);
+  lo = __low2half(h);
+  hi = __high2half(h);
+}
+
+template <class L, int COLL, class TS, int V, int XC>
+XLBN_DEV void step_body_pk(const StepParams<TS>& p, const int x, const int y, const int z0) {
+  static_assert(V % 2 == 0, "pair path needs an even number of cells per thread");
+  constexpr int Q = L::Q, NP = V / 2;
+  const unsigned nz = (unsigned)p.nz;
+  const unsigned xoff = (unsigned)x * (unsigned)p.plane;
+  const unsigned row_c = xoff + (unsigned)y * nz;
+  const unsigned row_m = xoff + (unsigned)(y == 0 ? p.ny - 1 : y - 1) * nz;
+  const unsigned row_p = xoff + (unsigned)(y == p.ny - 1 ? 0 : y + 1) * nz;
+  const unsigned z_lo = (z0 == 0) ? nz - 1 : (unsigned)z0 - 1;
+  const unsigned z_hi = ((unsigned)z0 + V >= nz) ? 0u : (unsigned)z0 + V;
+  const unsigned cell = row_c + (unsigned)z0;
+
+  const Pack<uint8_t, V> ids = gload<uint8_t, V>(p.bc + cell);
+  bool any_solid = false, all_solid = true, any_bc = false;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    any_solid |= (ids.v[v] == 255);
+    all_solid &= (ids.v[v] == 255);
+    any_bc |= (ids.v[v] != 0);
+  }
+  if (all_solid) return;
+
+  f32x2 f[NP][Q];
+  XLBN_FOR(Q, l)
+    constexpr int cx = L::ck(0, l), cy = L::ck(1, l), cz = L::ck(2, l);
+    constexpr int tab = (cx == 1 && (XC & 1)) ? 1 : ((cx == -1 && (XC & 2)) ? 2 : 0);
+    const TS* base = p.pull[tab][l];
+    const unsigned row = (cy == 1 ? row_m : (cy == -1 ? row_p : row_c));
+    const Pack<TS, V> a = gload<TS, V>(base + (row + (unsigned)z0));
+    if constexpr (cz == 0) {
+#pragma unroll
+      for (int j = 0; j < NP; ++j) f[j][l] = pair_up<TS>(a.v[2 * j], a.v[2 * j + 1]);
+    } else if constexpr (cz == 1) {  // out[z] = in[z - 1]
+      const Pack<TS, 1> e = gload<TS, 1>(base + (row + z_lo));
+      f[0][l] = pair_up<TS>(e.v[0], a.v[0]);
+#pragma unroll
+      for (int j = 1; j < NP; ++j) f[j][l] = pair_up<TS>(a.v[2 * j - 1], a.v[2 * j]);
+    } else {  // out[z] = in[z + 1]
+      const Pack<TS, 1> e = gload<TS, 1>(base + (row + z_hi));
+#pragma unroll
+      for (int j = 0; j < NP - 1; ++j) f[j][l] = pair_up<TS>(a.v[2 * j + 1], a.v[2 * j + 2]);
+      f[NP - 1][l] = pair_up<TS>(a.v[V - 1], e.v[0]);
+    }
+  XLBN_END
+
+  if (!any_bc) {
+    const f32x2 omega((float)p.omega);
+#pragma unroll
+    for (int j = 0; j < NP; ++j) collide_cell<L, COLL, f32x2, true>(f[j], omega);
+    XLBN_FOR(Q, l)
+      Pack<TS, V> a;
+#pragma unroll
+      for (int j = 0; j < NP; ++j) pair_down<TS>(f[j][l], a.v[2 * j], a.v[2 * j + 1]);
+      gstore<TS, V>(p.push[l] + cell, a);
+      if constexpr (L::ck(0, l) == 1 && (XC & 2)) {
+        if (p.peer_hi[l]) gstore<TS, V>(p.peer_hi[l] + cell, a);
+      } else if constexpr (L::ck(0, l) == -1 && (XC & 1)) {
+        if (p.peer_lo[l]) gstore<TS, V>(p.peer_lo[l] + cell, a);
+      }
+    XLBN_END
+    return;
+  }
+  // threads with boundary cells: unpack and take the scalar boundary tail
+  float fs[V][Q];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    XLBN_FOR(Q, l)
+      fs[2 * j][l] = f[j][l].v.x;
+      fs[2 * j + 1][l] = f[j][l].v.y;
+    XLBN_END
+  }
+  bc_tail<L, COLL, float, TS, V, XC>(p, ids, x, y, z0, cell, any_solid, fs);
+}
+
+template <class L, int COLL, class TC, class TS, int V, bool PK>
+__global__ void __launch_bounds__(StepTraits<L, COLL, TC, TS, V, PK>::kThreads, StepTraits<L, COLL, TC, TS, V, PK>::kMinBlocks)
     step_kernel(const __grid_constant__ StepParams<TS> p) {
   const int zv = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -398,16 +504,23 @@ __global__ void __launch_bounds__(StepTraits<L, COLL, TC, TS, V>::kThreads, Step
   if (z0 >= p.nz || y >= p.ny) return;
   // block-uniform dispatch on the x-plane class: interior planes carry no ghost / wrap logic at all
   const bool first = (x == 0), last = (x == p.nx - 1);
-  if (!first && !last) step_body<L, COLL, TC, TS, V, 0>(p, x, y, z0);
-  else if (first && !last) step_body<L, COLL, TC, TS, V, 1>(p, x, y, z0);
-  else if (last && !first) step_body<L, COLL, TC, TS, V, 2>(p, x, y, z0);
-  else step_body<L, COLL, TC, TS, V, 3>(p, x, y, z0);
+  if constexpr (PK) {
+    if (!first && !last) step_body_pk<L, COLL, TS, V, 0>(p, x, y, z0);
+    else if (first && !last) step_body_pk<L, COLL, TS, V, 1>(p, x, y, z0);
+    else if (last && !first) step_body_pk<L, COLL, TS, V, 2>(p, x, y, z0);
+    else step_body_pk<L, COLL, TS, V, 3>(p, x, y, z0);
+  } else {
+    if (!first && !last) step_body<L, COLL, TC, TS, V, 0>(p, x, y, z0);
+    else if (first && !last) step_body<L, COLL, TC, TS, V, 1>(p, x, y, z0);
+    else if (last && !first) step_body<L, COLL, TC, TS, V, 2>(p, x, y, z0);
+    else step_body<L, COLL, TC, TS, V, 3>(p, x, y, z0);
+  }
 }
 
 // ---- host-side launch ------------------------------------------------------------------------------------------------
-template <class L, int COLL, class TC, class TS, int V>
+template <class L, int COLL, class TC, class TS, int V, bool PK = false>
 int launch_step_v(const StepParams<TS>& p, int x_count, cudaStream_t stream) {
-  constexpr int T = StepTraits<L, COLL, TC, TS, V>::kThreads;
+  constexpr int T = StepTraits<L, COLL, TC, TS, V, PK>::kThreads;
   const int nzv = (p.nz + V - 1) / V;
   int bx = 32;
   while (bx < nzv && bx < T) bx *= 2;
@@ -415,7 +528,7 @@ int launch_step_v(const StepParams<TS>& p, int x_count, cudaStream_t stream) {
   dim3 block(bx, by, 1);
   dim3 grid((nzv + bx - 1) / bx, (p.ny + by - 1) / by, x_count);
   if (grid.y > 65535u || grid.z > 65535u) return fail(XLBN_E_SHAPE, "grid too large for launch: ny=%d x_count=%d", p.ny, x_count);
-  step_kernel<L, COLL, TC, TS, V><<<grid, block, 0, stream>>>(p);
+  step_kernel<L, COLL, TC, TS, V, PK><<<grid, block, 0, stream>>>(p);
   XLBN_LAUNCH_OK("step_kernel launch");
   return 0;
 }
@@ -436,21 +549,29 @@ inline int pick_cells_per_thread(int requested, int dflt, int esize, int nz, con
   return v;
 }
 
+// requested_v: 0 = library default; 1, 2, 4, 8 = scalar path with that many cells per thread; 102, 104 = packed pair
+// path (fp32 compute only) with 2 / 4 cells per thread.
 template <class L, int COLL, class TC, class TS>
 int launch_step(const StepParams<TS>& p, int x_count, int requested_v, const void* f0, const void* f1, const void* g0, const void* g1,
                 const void* o0, const void* o1, cudaStream_t stream) {
-  // defaults chosen on B200 (profiles/): see DESIGN.md "cells per thread"
-  constexpr int dflt = (sizeof(TS) == 2) ? 2 : 1;
-  const int v = pick_cells_per_thread(requested_v, dflt, (int)sizeof(TS), p.nz, p.bc, {f0, f1, g0, g1, o0, o1});
+  constexpr bool can_pack = sizeof(TC) == 4 && sizeof(TS) <= 4;
+  // defaults selected on B200 (profiles/)
+  int req = requested_v;
+  if (req == 0) req = 1;  // one cell per thread at maximum residency won every comparison on B200 (profiles/r1_bench_matrix2.txt)
+  bool packed = req >= 100;
+  if (packed && !can_pack) return fail(XLBN_E_ARG, "cells_per_thread = %d: the packed pair path needs fp32 compute and fp32/fp16 storage", req);
+  int v = pick_cells_per_thread(packed ? req - 100 : req, 1, (int)sizeof(TS), p.nz, p.bc, {f0, f1, g0, g1, o0, o1});
+  if (packed && v < 2) packed = false;  // nz odd or misaligned: scalar fallback
+  if constexpr (can_pack) {
+    if (packed) return launch_step_v<L, COLL, TC, TS, 2, true>(p, x_count, stream);  // wider pair variants spill (profiles/)
+  }
   switch (v) {
     case 1: return launch_step_v<L, COLL, TC, TS, 1>(p, x_count, stream);
     case 2: return launch_step_v<L, COLL, TC, TS, 2>(p, x_count, stream);
-    case 4:
+    default:  // 4 and 8 (8 is served by the 4-wide variant; it never won on B200)
       if constexpr (sizeof(TS) <= 4) return launch_step_v<L, COLL, TC, TS, 4>(p, x_count, stream);
-    case 8:
-      if constexpr (sizeof(TS) <= 2) return launch_step_v<L, COLL, TC, TS, 8>(p, x_count, stream);
+      else return launch_step_v<L, COLL, TC, TS, 2>(p, x_count, stream);
   }
-  return fail(XLBN_E_ARG, "cells_per_thread = %d not available for this store dtype", v);
 }
 
 // One entry per (lattice, collision); dispatches on (compute, store) dtype.  Defined in step_inst_*.cu.
@@ -487,7 +608,7 @@ int run_step_typed(const StepCall& c) {
   const long long plane = (long long)c.ny * c.nz;
   const long long n = plane * c.nx;
   if (n >= (1LL << 32)) return fail(XLBN_E_SHAPE, "more than 2^32 cells per slab (%lld): split the domain across GPUs", n);
-  static_for<L::Q>([&](auto l_) {
+  static_for_host<L::Q>([&](auto l_) {
     constexpr int l = decltype(l_)::value;
     constexpr int cx = L::ck(0, l);
     const TS* pop = f0 + (long long)l * n;
