@@ -181,6 +181,12 @@ int xlbn_collide(int lattice, int collision, int compute_dtype, const void* f, i
 int xlbn_bc_apply(int lattice, int compute_dtype, const xlbn_bc_desc* bc, const void* f_pre, void* f_post, int dtype,
                   const uint8_t* bc_mask, const uint8_t* missing, const int32_t dims[3], void* stream);
 
+/* MomentumTransfer (operator/force/momentum_transfer.py:51-90, 108-176): net momentum-exchange force on the solid
+ * behind the no-slip BC `bc`, summed over its edge cells.  f0 = post-collision populations, f1 = the second buffer
+ * (only read for the aux value of Zou-He-type BCs; may be NULL).  force: device double[3], overwritten. */
+int xlbn_momentum_transfer(int lattice, int compute_dtype, const xlbn_bc_desc* bc, const void* f0, const void* f1, int dtype,
+                           const uint8_t* bc_mask, const uint8_t* missing, const int32_t dims[3], double* force, void* stream);
+
 /* ---- x-slab halo (multi-GPU; one process per GPU) ------------------------------------------------------------- */
 /* Replaces the two lax.ppermute collectives of distribute.py:23-44 / parallel_operator.py:68-80.
  * Ghost storage per slab: 2 parities x 2 faces x n_dir x ny x nz store-dtype values (n_dir = 5 / 9 / 3), plus two

@@ -548,6 +548,18 @@ def initialize_eq(shape, lat: Lattice, policy="FP32FP32", rho=None, u=None):
     return equilibrium(rho, u, lat).astype(sdt)
 
 
+def momentum_transfer(bc: BC, f_post_collision, bc_mask, missing, lat: Lattice, flavor="jax"):
+    """Net momentum-exchange force on the solid behind the no-slip BC  (force/momentum_transfer.py:51-90)."""
+    f_pc = f_post_collision
+    f_ps = apply_bc(bc, f_pc, stream(f_pc, lat), bc_mask, missing, lat, flavor)
+    boundary = _bmask(bc_mask, bc.id, lat.q)
+    is_edge = np.logical_and(boundary, ~missing[0])
+    phi = f_pc[lat.opp] + f_ps
+    phi = np.where(np.logical_and(missing, is_edge), phi, f_pc.dtype.type(0.0))
+    force = np.tensordot(lat.c[:, lat.opp].astype(f_pc.dtype), phi, axes=(-1, 0))
+    return force.sum(axis=tuple(range(1, lat.d + 1)))
+
+
 # --------------------------------------------------------------------------------------------
 # x-slab halo exchange emulation  (distribute/distribute.py:23-44)
 # --------------------------------------------------------------------------------------------

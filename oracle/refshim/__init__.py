@@ -124,6 +124,8 @@ def _wrap_fn(name):
     def wrapped(*args, **kwargs):
         args = _promote_inputs(tuple(_unwrap(a) for a in args))
         kwargs = {k: _unwrap(v) for k, v in kwargs.items()}
+        if "axis" in kwargs and hasattr(kwargs["axis"], "__next__"):  # jax accepts any iterable of axes
+            kwargs["axis"] = tuple(kwargs["axis"])
         return _finish(fn(*args, **kwargs))
 
     wrapped.__name__ = name

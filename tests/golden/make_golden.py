@@ -66,7 +66,7 @@ def pack_bits(missing):
     return sum(m[l] << np.uint32(l) for l in range(m.shape[0])).astype(np.uint32)
 
 
-def run_and_save(name, meta, stepper, bcs_meta, steps, omega, initializer=None):
+def run_and_save(name, meta, stepper, bcs_meta, steps, omega, initializer=None, force_bc=None):
     f_0, f_1, bc_mask, missing = stepper.prepare_fields(initializer=initializer)
     f_init = np.asarray(f_0).copy()
     for i in range(steps):
@@ -85,6 +85,11 @@ def run_and_save(name, meta, stepper, bcs_meta, steps, omega, initializer=None):
     out["missing_bits"] = pack_bits(missing)
     out["rho"] = np.asarray(rho)
     out["u"] = np.asarray(u)
+    if force_bc is not None:  # reference MomentumTransfer (operator/force/momentum_transfer.py:51-90) on the final state
+        from xlb.operator.force.momentum_transfer import MomentumTransfer
+
+        out["force"] = np.asarray(MomentumTransfer(force_bc)(f_0, f_1, bc_mask, missing))
+        out["force_bc"] = np.int64(stepper.boundary_conditions.index(force_bc))
     assert not np.isnan(out["f_final"].astype(np.float64)).any(), name
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
@@ -161,7 +166,7 @@ def sphere(name, lattice, policy, shape, steps, collision, omega=1.6, outlet="ou
         out_meta,
         dict(kind="halfway", id=bc_sph.id, indices=np.array(sph)),
     ]
-    run_and_save(name, dict(lattice=lattice, policy=policy, collision=collision, shape=np.array(shape)), stepper, meta, steps, omega)
+    run_and_save(name, dict(lattice=lattice, policy=policy, collision=collision, shape=np.array(shape)), stepper, meta, steps, omega, force_bc=bc_sph)
 
 
 def periodic(name, lattice, policy, shape, steps, collision, omega):

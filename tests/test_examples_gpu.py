@@ -28,3 +28,10 @@ def test_sphere_kbc_script(tmp_path):
     os.environ["XLB_OUT_PREFIX"] = env_prefix
     out = run("examples/sphere_kbc.py", "128", "32", "32", "200")
     assert "MLUPS" in out and os.path.exists(env_prefix + "_0000200.pgm")
+
+
+@pytest.mark.parametrize("collision", ["BGK", "KBC"])
+def test_cavity_2d_script(tmp_path, collision):
+    os.environ["XLB_OUT_PREFIX"] = str(tmp_path / "c2d")
+    out = run("examples/cavity_2d.py", "128", "2000", collision)
+    assert "max |u|" in out and os.path.exists(str(tmp_path / "c2d") + "_0002000.pgm")

@@ -222,3 +222,20 @@ def test_both_masker_algorithms_bit_exact(flavor, backend, lattice, shape):
     bc_mask, missing_mask = IndicesBoundaryMasker()(bcs, bc_mask, missing_mask)
     assert np.array_equal(bc_mask.numpy().reshape(bm.shape), bm)
     assert np.array_equal(missing_mask.numpy().reshape(mm.shape), mm)
+
+
+@pytest.mark.parametrize("backend", [ComputeBackend.WARP, ComputeBackend.JAX])
+@pytest.mark.parametrize("name", ["sphere_d3q27_kbc_fp32", "sphere_d3q19_bgk_fp32", "sphere_d3q27_bgk_regpressure_fp64"])
+def test_momentum_transfer_matches_reference_vectors(name, backend):
+    """Drag / lift of the sphere by momentum exchange, against the value the reference's MomentumTransfer computed."""
+    from common import load_golden, native_case
+    from xlb_b200.operator.force import MomentumTransfer
+
+    g = load_golden(name)
+    stepper, f_0, f_1, bc_mask, missing_mask = native_case(g, backend=backend.name)
+    f_0.copy_(torch.as_tensor(g["f_final"]).reshape(f_0.shape))
+    bc = stepper.boundary_conditions[int(g["force_bc"])]
+    force = MomentumTransfer(bc)(f_0, f_1, bc_mask, missing_mask)
+    force = force.numpy() if hasattr(force, "numpy") and not isinstance(force, np.ndarray) else np.asarray(force)
+    assert force.shape == (3,)
+    assert np.allclose(force, g["force"], rtol=2e-5, atol=1e-7), (force, g["force"])

@@ -52,3 +52,16 @@ def test_operator_vectors(lattice):
     else:
         with pytest.raises(NotImplementedError):
             O.collide_kbc(f, feq2, r2, lat, 1.7)
+
+
+@pytest.mark.parametrize("name", [c for c in STEP_CASES if c.startswith("sphere")])
+def test_momentum_transfer_vectors(name):
+    """MomentumTransfer (operator/force/momentum_transfer.py:51-90) on the final state of the sphere cases."""
+    from common import oracle_bcs
+
+    g = load_golden(name)
+    lat = O.Lattice(g["lattice"])
+    cdt, _ = O.policy_dtypes(g["policy"])
+    bc = oracle_bcs(g)[int(g["force_bc"])]
+    force = O.momentum_transfer(bc, g["f_final"].astype(cdt), g["bc_mask"], unpack_bits(g["missing_bits"], lat.q), lat)
+    assert np.allclose(force, g["force"], rtol=1e-6, atol=1e-9)

@@ -24,6 +24,7 @@ import xlb_b200.operator.boundary_condition
 import xlb_b200.operator.boundary_masker
 import xlb_b200.operator.macroscopic
 import xlb_b200.operator.stepper
+import xlb_b200.operator.force
 import xlb_b200.grid
 import xlb_b200.helper
 import xlb_b200.utils

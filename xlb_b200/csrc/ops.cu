@@ -134,6 +134,31 @@ __global__ void collide_kernel(const void* f, int f_dt, const void* feq, int feq
 
 // ---- Generic stand-alone boundary-condition kernel (boundary_condition.py:83-117) -------------------------------------
 // f_0 := f_pre array, f_1 := f_post array, exactly as the reference passes them to the functional.
+// bc_functional applies one BC's functional to one cell: f holds f_post on entry and the BC's result on exit.
+template <class L, class TC>
+__device__ __forceinline__ void bc_functional(const xlbn_bc_desc& bc, uint32_t miss, const void* fpre, int dt, TC aux, long long i, long long n,
+                                              TC (&f)[L::Q]) {
+  constexpr int Q = L::Q;
+  const int kind = bc.kind;
+  if (kind == XLBN_BC_EQUILIBRIUM) {
+    TC u[L::D];
+    XLBN_FOR(L::D, a) u[a] = (TC)bc.u[a]; XLBN_END
+    equilibrium<L, TC>((TC)bc.rho, u, f);
+  } else if (kind == XLBN_BC_FULLWAY_BOUNCE_BACK || bc_kind_needs_fpre(kind)) {
+    TC pre[Q];
+    XLBN_FOR(Q, l) pre[l] = load_as<TC>(fpre, dt, (long long)l * n + i); XLBN_END
+    if (kind == XLBN_BC_FULLWAY_BOUNCE_BACK) {
+      XLBN_FOR(Q, l) f[l] = pre[L::opp(l)]; XLBN_END
+    } else if (kind == XLBN_BC_DO_NOTHING) {
+      XLBN_FOR(Q, l) f[l] = pre[l]; XLBN_END
+    } else {
+      bc_take_opposite_of_pre<L, TC>(pre, miss, f);
+    }
+  } else if (bc_kind_needs_aux(kind)) {
+    bc_zouhe<L, TC>(kind, aux, miss, f);
+  }
+}
+
 template <class L, class TC>
 __global__ void bc_apply_kernel(xlbn_bc_desc bc, const void* fpre, void* fpost, int dt, const uint8_t* bc_mask, const uint8_t* missing,
                                 Dims d) {
@@ -146,26 +171,55 @@ __global__ void bc_apply_kernel(xlbn_bc_desc bc, const void* fpre, void* fpost, 
     f[l] = load_as<TC>(fpost, dt, (long long)l * d.n + i);
     if (missing[(long long)l * d.n + i]) miss |= (1u << l);
   XLBN_END
-  const int kind = bc.kind;
-  if (kind == XLBN_BC_EQUILIBRIUM) {
-    TC u[L::D];
-    XLBN_FOR(L::D, a) u[a] = (TC)bc.u[a]; XLBN_END
-    equilibrium<L, TC>((TC)bc.rho, u, f);
-  } else if (kind == XLBN_BC_FULLWAY_BOUNCE_BACK || bc_kind_needs_fpre(kind)) {
-    TC pre[Q];
-    XLBN_FOR(Q, l) pre[l] = load_as<TC>(fpre, dt, (long long)l * d.n + i); XLBN_END
-    if (kind == XLBN_BC_FULLWAY_BOUNCE_BACK) {
-      XLBN_FOR(Q, l) f[l] = pre[L::opp(l)]; XLBN_END
-    } else if (kind == XLBN_BC_DO_NOTHING) {
-      XLBN_FOR(Q, l) f[l] = pre[l]; XLBN_END
-    } else {
-      bc_take_opposite_of_pre<L, TC>(pre, miss, f);
-    }
-  } else if (bc_kind_needs_aux(kind)) {
-    const TC aux = load_as<TC>(fpost, dt, i);  // f_1[0, cell]  (bc_zouhe.py:302, 327)
-    bc_zouhe<L, TC>(kind, aux, miss, f);
-  }
+  const TC aux = load_as<TC>(fpost, dt, i);  // f_1[0, cell]  (bc_zouhe.py:302, 327)
+  bc_functional<L, TC>(bc, miss, fpre, dt, aux, i, d.n, f);
   XLBN_FOR(Q, l) store_as<TC>(fpost, dt, (long long)l * d.n + i, f[l]); XLBN_END
+}
+
+// ---- MomentumTransfer (force/momentum_transfer.py:108-176): momentum exchange over the edge cells of a no-slip BC -------
+// edge cell: bc id matches and the rest direction is not missing.  f_post_stream = pull(f_0) with the BC's functional
+// applied (f_pre = the cell's own f_0); m_d = sum over missing l of c[d, opp l] (f_0[opp l] + f_post_stream[l]).
+template <class L, class TC>
+__global__ void momentum_transfer_kernel(xlbn_bc_desc bc, const void* f0, const void* f1, int dt, const uint8_t* bc_mask,
+                                         const uint8_t* missing, Dims d, double* force) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int Q = L::Q;
+  double m[3] = {0.0, 0.0, 0.0};
+  if (i < d.n && bc_mask[i] == (uint8_t)bc.id && !missing[i]) {
+    const int z = (int)(i % d.nz);
+    const int y = (int)((i / d.nz) % d.ny);
+    const int x = (int)(i / ((long long)d.nz * d.ny));
+    TC fpc[Q], fps[Q];
+    uint32_t miss = 0;
+    XLBN_FOR(Q, l)
+      fpc[l] = load_as<TC>(f0, dt, (long long)l * d.n + i);
+      if (missing[(long long)l * d.n + i]) miss |= (1u << l);
+      int xs = x - L::ck(0, l), ys = y - L::ck(1, l), zs = z - L::ck(2, l);
+      xs = xs < 0 ? d.nx - 1 : (xs >= d.nx ? 0 : xs);
+      ys = ys < 0 ? d.ny - 1 : (ys >= d.ny ? 0 : ys);
+      zs = zs < 0 ? d.nz - 1 : (zs >= d.nz ? 0 : zs);
+      fps[l] = load_as<TC>(f0, dt, (long long)l * d.n + ((long long)xs * d.ny + ys) * d.nz + zs);
+    XLBN_END
+    const TC aux = f1 ? load_as<TC>(f1, dt, i) : TC(0);
+    bc_functional<L, TC>(bc, miss, f0, dt, aux, i, d.n, fps);
+    XLBN_FOR(Q, l)
+      if ((miss >> l) & 1u) {
+        const TC phi = fpc[L::opp(l)] + fps[l];
+        XLBN_FOR(L::D, a)
+          if constexpr (L::c(a, L::opp(l)) == 1) m[a] += (double)phi;
+          else if constexpr (L::c(a, L::opp(l)) == -1) m[a] -= (double)phi;
+        XLBN_END
+      }
+    XLBN_END
+  }
+  // warp reduction, then one atomic per warp and component
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    double v = m[a];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(force + a, v);
+  }
 }
 
 // ---- dispatch helpers ---------------------------------------------------------------------------------------------------
@@ -301,6 +355,22 @@ int xlbn_bc_apply(int lattice, int compute_dtype, const xlbn_bc_desc* bc, const 
   XLBN_LATTICE_SWITCH(lattice, XLBN_COMPUTE_SWITCH(compute_dtype, bc_apply_kernel<L, TC><<<grid_for(d.n), 256, 0, (cudaStream_t)stream>>>(
                                                                       b, f_pre, f_post, dtype, bc_mask, missing, d)));
   XLBN_LAUNCH_OK("bc_apply_kernel");
+  return 0;
+}
+
+int xlbn_momentum_transfer(int lattice, int compute_dtype, const xlbn_bc_desc* bc, const void* f0, const void* f1, int dtype,
+                           const uint8_t* bc_mask, const uint8_t* missing, const int32_t dims[3], double* force, void* stream) {
+  if (int e = check_dims(lattice, dims)) return e;
+  if (!bc || !f0 || !bc_mask || !missing || !force) return fail(XLBN_E_ARG, "xlbn_momentum_transfer: NULL argument");
+  XLBN_REQUIRE_FLOAT(dtype, "f_0");
+  if (bc->kind <= XLBN_BC_NONE || bc->kind > XLBN_BC_EXTRAPOLATION_OUTFLOW) return fail(XLBN_E_ARG, "xlbn_momentum_transfer: bad BC kind %d", bc->kind);
+  const Dims d = kernel_dims(lattice, dims);
+  const xlbn_bc_desc b = *bc;
+  cudaStream_t st = (cudaStream_t)stream;
+  XLBN_CUDA_OK(cudaMemsetAsync(force, 0, 3 * sizeof(double), st));
+  XLBN_LATTICE_SWITCH(lattice, XLBN_COMPUTE_SWITCH(compute_dtype, momentum_transfer_kernel<L, TC><<<grid_for(d.n), 256, 0, st>>>(
+                                                                      b, f0, f1, dtype, bc_mask, missing, d, force)));
+  XLBN_LAUNCH_OK("momentum_transfer_kernel");
   return 0;
 }
 

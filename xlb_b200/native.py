@@ -88,6 +88,7 @@ SIGNATURES = {
     "xlbn_second_moment": [_I, _I, _P, _I, _P, _I, Int3, _P],
     "xlbn_collide": [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _D, Int3, _P],
     "xlbn_bc_apply": [_I, _I, C.POINTER(BcDesc), _P, _P, _I, _P, _P, Int3, _P],
+    "xlbn_momentum_transfer": [_I, _I, C.POINTER(BcDesc), _P, _P, _I, _P, _P, Int3, _P, _P],
     "xlbn_halo_create": [_I, _I, _I, _I, C.POINTER(_P)],
     "xlbn_halo_destroy": [_P],
     "xlbn_halo_export": [_P, C.c_char_p],
