@@ -26,11 +26,15 @@ def test_step_matches_reference_vectors(name, backend):
     assert rel_err(f, g["f_final"]) <= RTOL[g["policy"]], f"{name}: rel err {rel_err(f, g['f_final']):.3e}"
 
 
-@pytest.mark.parametrize("v", [1, 2, 4, 8, 102, 104])  # 10x = packed fp32x2 pair path (falls back to scalar for fp64)
+@pytest.mark.parametrize("v", [1, 2, 4, 8, 102, 104, 202])  # 10x = packed fp32x2 pair path, 202 = half2-state path (FP32FP16 BGK)
 @pytest.mark.parametrize("name", ["cavity_d3q19_bgk_fp32", "cavity_d3q19_bgk_fp32fp16", "sphere_d3q27_kbc_fp32", "sphere_d3q27_bgk_regpressure_fp64", "cavity_d2q9_kbc_fp32"])
 def test_every_cells_per_thread_variant(name, v):
     """All vector widths of the kernel compute the same step (the library falls back when v does not divide nz)."""
     g = load_golden(name)
+    if v == 202 and not (g["policy"] == "FP32FP16" and g["collision"] == "BGK"):
+        with pytest.raises(Exception, match="FP32FP16 BGK only"):
+            native_run(g, cells_per_thread=v)
+        return
     if v >= 100 and g["policy"].startswith("FP64"):
         with pytest.raises(Exception, match="packed pair path"):
             native_run(g, cells_per_thread=v)

@@ -245,14 +245,16 @@ __device__ __noinline__ void bc_cell(const StepParams<TS>& p, int id, int x, int
 #define XLBN_ST_CS 0  // 1: st.global.cs (evict-first) for the population stores
 #endif
 
-template <class L, int COLL, class TC, class TS, int V, bool PK = false>
+template <class L, int COLL, class TC, class TS, int V, int MODE = 0>
 struct StepTraits {
+  static constexpr bool PK = MODE == 1;
   static constexpr int kThreads = 128;
   // Occupancy-first register budget (the kernel is latency-bound until ~48 warps/SM are resident, profiles/):
   // V*Q population registers (x2 for fp64) + collision temporaries + addresses.
   static constexpr int kW = (int)(sizeof(TC) / 4);
-  static constexpr int kRegs = PK ? V * L::Q + (COLL == XLBN_KBC ? 4 : 2) * L::Q + 29  // pair temporaries take two registers each
-                                  : V * L::Q * kW + (COLL == XLBN_KBC ? L::Q * kW + 24 : 24) + 5;
+  static constexpr int kRegs = MODE == 2 ? L::Q + 45  // populations stay packed as half2: q registers for two cells
+                               : PK      ? V * L::Q + (COLL == XLBN_KBC ? 4 : 2) * L::Q + 29  // pair temporaries take two registers each
+                                         : V * L::Q * kW + (COLL == XLBN_KBC ? L::Q * kW + 24 : 24) + 5;
   static constexpr int kMinBlocksRaw = 65536 / (kThreads * (kRegs > 255 ? 255 : kRegs));
   static constexpr int kMinBlocksAuto = kMinBlocksRaw < 1 ? 1 : (kMinBlocksRaw > 12 ? 12 : kMinBlocksRaw);
   static constexpr int kMinBlocks = XLBN_MINB_OVERRIDE > 0 ? XLBN_MINB_OVERRIDE : kMinBlocksAuto;
@@ -494,8 +496,103 @@ XLBN_DEV void step_body_pk(const StepParams<TS>& p, const int x, const int y, co
   bc_tail<L, COLL, float, TS, V, XC>(p, ids, x, y, z0, cell, any_solid, fs);
 }
 
-template <class L, int COLL, class TC, class TS, int V, bool PK>
-__global__ void __launch_bounds__(StepTraits<L, COLL, TC, TS, V, PK>::kThreads, StepTraits<L, COLL, TC, TS, V, PK>::kMinBlocks)
+
+// ---- half2-state pair path (FP32FP16, BGK): two cells per thread, populations kept as the loaded half2 words ---------------
+// The q post-stream populations of the two cells stay in q 32-bit registers (half2) — the storage format IS the register
+// format — and are widened to a fp32x2 pair on the fly twice: once to accumulate rho and u, once for equilibrium +
+// relaxation, whose result is narrowed (one F2FP) and stored immediately.  Live state: q + ~25 registers for two cells,
+// so the kernel keeps the residency of the one-cell path while issuing ~2.5x fewer instructions per cell (FADD2 / FMUL2 /
+// FFMA2 for both cells at once); the fp16 path is issue-bound otherwise (profiles/README.md).
+template <class L, int XC>
+XLBN_DEV void step_body_h2(const StepParams<__half>& p, const int x, const int y, const int z0) {
+  using TS = __half;
+  constexpr int Q = L::Q, V = 2;
+  const unsigned nz = (unsigned)p.nz;
+  const unsigned xoff = (unsigned)x * (unsigned)p.plane;
+  const unsigned row_c = xoff + (unsigned)y * nz;
+  const unsigned row_m = xoff + (unsigned)(y == 0 ? p.ny - 1 : y - 1) * nz;
+  const unsigned row_p = xoff + (unsigned)(y == p.ny - 1 ? 0 : y + 1) * nz;
+  const unsigned z_lo = (z0 == 0) ? nz - 1 : (unsigned)z0 - 1;
+  const unsigned z_hi = ((unsigned)z0 + V >= nz) ? 0u : (unsigned)z0 + V;
+  const unsigned cell = row_c + (unsigned)z0;
+
+  const Pack<uint8_t, V> ids = gload<uint8_t, V>(p.bc + cell);
+  const bool any_solid = (ids.v[0] == 255) | (ids.v[1] == 255);
+  const bool any_bc = (ids.v[0] != 0) | (ids.v[1] != 0);
+  if ((ids.v[0] == 255) & (ids.v[1] == 255)) return;
+
+  __half2 h[Q];
+  XLBN_FOR(Q, l)
+    constexpr int cx = L::ck(0, l), cy = L::ck(1, l), cz = L::ck(2, l);
+    constexpr int tab = (cx == 1 && (XC & 1)) ? 1 : ((cx == -1 && (XC & 2)) ? 2 : 0);
+    const TS* base = p.pull[tab][l];
+    const unsigned row = (cy == 1 ? row_m : (cy == -1 ? row_p : row_c));
+    const Pack<TS, 2> a = gload<TS, 2>(base + (row + (unsigned)z0));
+    if constexpr (cz == 0) {
+      h[l] = __halves2half2(a.v[0], a.v[1]);
+    } else if constexpr (cz == 1) {  // out[z] = in[z - 1]
+      const Pack<TS, 1> e = gload<TS, 1>(base + (row + z_lo));
+      h[l] = __halves2half2(e.v[0], a.v[0]);
+    } else {  // out[z] = in[z + 1]
+      const Pack<TS, 1> e = gload<TS, 1>(base + (row + z_hi));
+      h[l] = __halves2half2(a.v[1], e.v[0]);
+    }
+  XLBN_END
+
+  if (!any_bc) {
+    // moments (macroscopic.py:43-47) over the widened pairs
+    f32x2 rho(0.0f), u[L::D];
+    XLBN_FOR(L::D, d) u[d] = f32x2(0.0f); XLBN_END
+    XLBN_FOR(Q, l)
+      const f32x2 f(__half22float2(h[l]));
+      rho += f;
+      XLBN_FOR(L::D, d)
+        if constexpr (L::c(d, l) == 1) u[d] += f;
+        else if constexpr (L::c(d, l) == -1) u[d] -= f;
+      XLBN_END
+    XLBN_END
+    const f32x2 inv = rcp_(rho);
+    XLBN_FOR(L::D, d) u[d] = u[d] * inv; XLBN_END
+    f32x2 uu = u[0] * u[0];
+    XLBN_FOR(L::D - 1, d) uu = fma_(u[d + 1], u[d + 1], uu); XLBN_END
+    const f32x2 usqr = f32x2(1.5f) * uu;
+    const f32x2 omega((float)p.omega);
+    // equilibrium + BGK relaxation per population (quadratic_equilibrium.py:35-60, bgk.py:30-34), narrowed and stored at once
+    XLBN_FOR(Q, l)
+      const f32x2 f(__half22float2(h[l]));
+      f32x2 cu(0.0f);
+      XLBN_FOR(L::D, d)
+        if constexpr (L::c(d, l) == 1) cu += u[d];
+        else if constexpr (L::c(d, l) == -1) cu -= u[d];
+      XLBN_END
+      cu *= f32x2(3.0f);
+      const f32x2 feq = rho * f32x2(L::w(l)) * (fma_(cu, fma_(f32x2(0.5f), cu, f32x2(1.0f)), f32x2(1.0f)) - usqr);
+      const f32x2 out = fma_(-omega, f - feq, f);
+      const __half2 o = __float22half2_rn(out.v);
+      Pack<TS, 2> a;
+      a.v[0] = __low2half(o);
+      a.v[1] = __high2half(o);
+      gstore<TS, 2>(p.push[l] + cell, a);
+      if constexpr (L::ck(0, l) == 1 && (XC & 2)) {
+        if (p.peer_hi[l]) gstore<TS, 2>(p.peer_hi[l] + cell, a);
+      } else if constexpr (L::ck(0, l) == -1 && (XC & 1)) {
+        if (p.peer_lo[l]) gstore<TS, 2>(p.peer_lo[l] + cell, a);
+      }
+    XLBN_END
+    return;
+  }
+  // threads with boundary cells: widen and take the scalar boundary tail
+  float fs[V][Q];
+  XLBN_FOR(Q, l)
+    const float2 f = __half22float2(h[l]);
+    fs[0][l] = f.x;
+    fs[1][l] = f.y;
+  XLBN_END
+  bc_tail<L, XLBN_BGK, float, TS, V, XC>(p, ids, x, y, z0, cell, any_solid, fs);
+}
+
+template <class L, int COLL, class TC, class TS, int V, int MODE>
+__global__ void __launch_bounds__(StepTraits<L, COLL, TC, TS, V, MODE>::kThreads, StepTraits<L, COLL, TC, TS, V, MODE>::kMinBlocks)
     step_kernel(const __grid_constant__ StepParams<TS> p) {
   const int zv = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -504,7 +601,12 @@ __global__ void __launch_bounds__(StepTraits<L, COLL, TC, TS, V, PK>::kThreads, 
   if (z0 >= p.nz || y >= p.ny) return;
   // block-uniform dispatch on the x-plane class: interior planes carry no ghost / wrap logic at all
   const bool first = (x == 0), last = (x == p.nx - 1);
-  if constexpr (PK) {
+  if constexpr (MODE == 2) {
+    if (!first && !last) step_body_h2<L, 0>(p, x, y, z0);
+    else if (first && !last) step_body_h2<L, 1>(p, x, y, z0);
+    else if (last && !first) step_body_h2<L, 2>(p, x, y, z0);
+    else step_body_h2<L, 3>(p, x, y, z0);
+  } else if constexpr (MODE == 1) {
     if (!first && !last) step_body_pk<L, COLL, TS, V, 0>(p, x, y, z0);
     else if (first && !last) step_body_pk<L, COLL, TS, V, 1>(p, x, y, z0);
     else if (last && !first) step_body_pk<L, COLL, TS, V, 2>(p, x, y, z0);
@@ -518,9 +620,9 @@ __global__ void __launch_bounds__(StepTraits<L, COLL, TC, TS, V, PK>::kThreads, 
 }
 
 // ---- host-side launch ------------------------------------------------------------------------------------------------
-template <class L, int COLL, class TC, class TS, int V, bool PK = false>
+template <class L, int COLL, class TC, class TS, int V, int MODE = 0>
 int launch_step_v(const StepParams<TS>& p, int x_count, cudaStream_t stream) {
-  constexpr int T = StepTraits<L, COLL, TC, TS, V, PK>::kThreads;
+  constexpr int T = StepTraits<L, COLL, TC, TS, V, MODE>::kThreads;
   const int nzv = (p.nz + V - 1) / V;
   int bx = 32;
   while (bx < nzv && bx < T) bx *= 2;
@@ -528,7 +630,7 @@ int launch_step_v(const StepParams<TS>& p, int x_count, cudaStream_t stream) {
   dim3 block(bx, by, 1);
   dim3 grid((nzv + bx - 1) / bx, (p.ny + by - 1) / by, x_count);
   if (grid.y > 65535u || grid.z > 65535u) return fail(XLBN_E_SHAPE, "grid too large for launch: ny=%d x_count=%d", p.ny, x_count);
-  step_kernel<L, COLL, TC, TS, V, PK><<<grid, block, 0, stream>>>(p);
+  step_kernel<L, COLL, TC, TS, V, MODE><<<grid, block, 0, stream>>>(p);
   XLBN_LAUNCH_OK("step_kernel launch");
   return 0;
 }
@@ -550,20 +652,30 @@ inline int pick_cells_per_thread(int requested, int dflt, int esize, int nz, con
 }
 
 // requested_v: 0 = library default; 1, 2, 4, 8 = scalar path with that many cells per thread; 102, 104 = packed pair
-// path (fp32 compute only) with 2 / 4 cells per thread.
+// path (fp32 compute only); 202 = half2-state pair path (FP32FP16 BGK only: the two cells' populations stay packed as
+// half2 registers and are converted on the fly, once for the moments and once for the relaxation).
 template <class L, int COLL, class TC, class TS>
 int launch_step(const StepParams<TS>& p, int x_count, int requested_v, const void* f0, const void* f1, const void* g0, const void* g1,
                 const void* o0, const void* o1, cudaStream_t stream) {
   constexpr bool can_pack = sizeof(TC) == 4 && sizeof(TS) <= 4;
   // defaults selected on B200 (profiles/)
   int req = requested_v;
-  if (req == 0) req = 1;  // one cell per thread at maximum residency won every comparison on B200 (profiles/r1_bench_matrix2.txt)
+  constexpr bool can_h2 = sizeof(TC) == 4 && sizeof(TS) == 2 && COLL == XLBN_BGK;
+  if (req == 0) req = can_h2 ? 202 : 1;
+  if (req == 202) {
+    if constexpr (can_h2) {
+      if (pick_cells_per_thread(2, 1, (int)sizeof(TS), p.nz, p.bc, {f0, f1, g0, g1, o0, o1}) == 2) return launch_step_v<L, COLL, TC, TS, 2, 2>(p, x_count, stream);
+      req = 1;  // odd nz or misaligned arrays: scalar fallback
+    } else {
+      return fail(XLBN_E_ARG, "cells_per_thread = 202: the half2-state path exists for FP32FP16 BGK only");
+    }
+  }  // one cell per thread at maximum residency won every comparison on B200 (profiles/r1_bench_matrix2.txt)
   bool packed = req >= 100;
   if (packed && !can_pack) return fail(XLBN_E_ARG, "cells_per_thread = %d: the packed pair path needs fp32 compute and fp32/fp16 storage", req);
   int v = pick_cells_per_thread(packed ? req - 100 : req, 1, (int)sizeof(TS), p.nz, p.bc, {f0, f1, g0, g1, o0, o1});
   if (packed && v < 2) packed = false;  // nz odd or misaligned: scalar fallback
   if constexpr (can_pack) {
-    if (packed) return launch_step_v<L, COLL, TC, TS, 2, true>(p, x_count, stream);  // wider pair variants spill (profiles/)
+    if (packed) return launch_step_v<L, COLL, TC, TS, 2, 1>(p, x_count, stream);  // wider pair variants spill (profiles/)
   }
   switch (v) {
     case 1: return launch_step_v<L, COLL, TC, TS, 1>(p, x_count, stream);
