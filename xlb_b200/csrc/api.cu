@@ -1,4 +1,6 @@
 // extern "C" entry points of the hot path: stepper handle + one fused step (include/xlb_b200.h).
+#include <cmath>
+
 #include "halo.cuh"
 #include "step_kernel.cuh"
 
@@ -6,6 +8,8 @@ struct xlbn_stepper {
   int lattice, collision, compute_dtype, store_dtype, cells_per_thread;
   bool needs_missing;
   uint8_t kinds[256];    // host copy: bc id -> kind
+  bool has_equilibrium_bc;
+  double eq_omega;       // omega the EquilibriumBC constants in the table were computed for (NaN = never)
   xlbn::BcEntry* table;  // device, 256 entries
   int device;
 };
@@ -79,7 +83,12 @@ int xlbn_stepper_create(const xlbn_stepper_desc* desc, xlbn_stepper** out) {
   s->cells_per_thread = cpt;
   s->needs_missing = needs_missing;
   s->table = nullptr;
-  for (int i = 0; i < 256; ++i) s->kinds[i] = (uint8_t)host[i].kind;
+  s->has_equilibrium_bc = false;
+  for (int i = 0; i < 256; ++i) {
+    s->kinds[i] = (uint8_t)host[i].kind;
+    s->has_equilibrium_bc |= host[i].kind == XLBN_BC_EQUILIBRIUM;
+  }
+  s->eq_omega = nan("");
   cudaError_t e = cudaGetDevice(&s->device);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->table), sizeof(host));
   if (e == cudaSuccess) e = cudaMemcpy(s->table, host, sizeof(host), cudaMemcpyHostToDevice);
@@ -119,6 +128,9 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
   c.bc = bc_mask;
   c.miss = missing_bits;
   c.table = s->table;
+  c.table_rw = s->table;
+  // EquilibriumBC constants (read by the FP32FP16 pair path only) follow omega; refreshing them synchronises the stream
+  c.eq_omega_state = s->has_equilibrium_bc ? &s->eq_omega : nullptr;
   c.kinds = s->kinds;
   c.omega = omega;
   c.stream = (cudaStream_t)stream;

@@ -27,14 +27,18 @@
 
 namespace xlbn {
 
+constexpr int kMaxQ = 27;
+
 struct BcEntry {
   int kind;
   int pad;
   double rho;
   double u[3];
+  // EquilibriumBC only: the cell's complete update, collide(feq(rho, u)), which does not depend on the pulled populations.
+  // Refreshed by bc_precompute_kernel whenever omega changes; read by the half2-state pair path.
+  float eq_out[kMaxQ];
+  int pad2;
 };
-
-constexpr int kMaxQ = 27;
 
 // Kernel parameters.  Everything that depends only on (population, x-plane class) is folded into pointer tables on the
 // host, so that inside the kernel an address is ONE table entry (constant bank) + ONE 32-bit per-thread element offset
@@ -497,6 +501,86 @@ XLBN_DEV void step_body_pk(const StepParams<TS>& p, const int x, const int y, co
 }
 
 
+// One thread per bc id: EquilibriumBC entries get their constant cell update (same device functions as every other path).
+template <class L, int COLL>
+__global__ void bc_precompute_kernel(BcEntry* table, float omega) {
+  const int id = threadIdx.x;
+  if (id >= 256 || table[id].kind != XLBN_BC_EQUILIBRIUM) return;
+  float u[L::D], f[L::Q];
+  XLBN_FOR(L::D, d) u[d] = (float)table[id].u[d]; XLBN_END
+  equilibrium<L, float>((float)table[id].rho, u, f);
+  collide_cell<L, COLL, float, kFast<COLL, float>>(f, omega);
+  XLBN_FOR(L::Q, l) table[id].eq_out[l] = f[l]; XLBN_END
+}
+
+// moments + equilibrium + BGK + narrow + store for the two cells of a half2-state thread.  WITH_BC: per-half handling of
+// FullwayBounceBack (bit copy of the opposite population's half; fp16 -> fp32 -> fp16 is exact) and EquilibriumBC cells
+// (the precomputed constant update, BcEntry::eq_out); id_lo / id_hi = bc ids of the two cells.
+template <class L, int XC, bool WITH_BC>
+XLBN_DEV void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L::Q], const unsigned cell, const int id_lo, const int id_hi) {
+  using TS = __half;
+  constexpr int Q = L::Q;
+  bool eq_lo = false, eq_hi = false, fw_lo = false, fw_hi = false;
+  const float* out_lo = nullptr;
+  const float* out_hi = nullptr;
+  if constexpr (WITH_BC) {
+    const int k_lo = id_lo ? (int)p.kinds[id_lo] : 0, k_hi = id_hi ? (int)p.kinds[id_hi] : 0;
+    eq_lo = k_lo == XLBN_BC_EQUILIBRIUM;
+    eq_hi = k_hi == XLBN_BC_EQUILIBRIUM;
+    fw_lo = k_lo == XLBN_BC_FULLWAY_BOUNCE_BACK;
+    fw_hi = k_hi == XLBN_BC_FULLWAY_BOUNCE_BACK;
+    out_lo = p.table[id_lo].eq_out;
+    out_hi = p.table[id_hi].eq_out;
+  }
+  // moments (macroscopic.py:43-47)
+  f32x2 rho(0.0f), u[L::D];
+  XLBN_FOR(L::D, d) u[d] = f32x2(0.0f); XLBN_END
+  XLBN_FOR(Q, l)
+    const f32x2 f(__half22float2(h[l]));
+    rho += f;
+    XLBN_FOR(L::D, d)
+      if constexpr (L::c(d, l) == 1) u[d] += f;
+      else if constexpr (L::c(d, l) == -1) u[d] -= f;
+    XLBN_END
+  XLBN_END
+  const f32x2 inv = rcp_(rho);
+  XLBN_FOR(L::D, d) u[d] = u[d] * inv; XLBN_END
+  f32x2 uu = u[0] * u[0];
+  XLBN_FOR(L::D - 1, d) uu = fma_(u[d + 1], u[d + 1], uu); XLBN_END
+  const f32x2 usqr = f32x2(1.5f) * uu;
+  const f32x2 omega((float)p.omega);
+  // equilibrium + BGK relaxation per population (quadratic_equilibrium.py:35-60, bgk.py:30-34), narrowed and stored at once
+  XLBN_FOR(Q, l)
+    const f32x2 f(__half22float2(h[l]));
+    f32x2 cu(0.0f);
+    XLBN_FOR(L::D, d)
+      if constexpr (L::c(d, l) == 1) cu += u[d];
+      else if constexpr (L::c(d, l) == -1) cu -= u[d];
+    XLBN_END
+    cu *= f32x2(3.0f);
+    const f32x2 feq = rho * f32x2(L::w(l)) * (fma_(cu, fma_(f32x2(0.5f), cu, f32x2(1.0f)), f32x2(1.0f)) - usqr);
+    f32x2 out = fma_(-omega, f - feq, f);
+    if constexpr (WITH_BC) {  // bc_equilibrium.py:76-86 followed by the ordinary collision = a per-BC constant
+      if (eq_lo) out.v.x = out_lo[l];
+      if (eq_hi) out.v.y = out_hi[l];
+    }
+    __half2 o = __float22half2_rn(out.v);
+    if constexpr (WITH_BC) {  // bc_fullway_bounce_back.py:60-72: out[l] = f_post_stream[opp l]
+      if (fw_lo) o = __halves2half2(__low2half(h[L::opp(l)]), __high2half(o));
+      if (fw_hi) o = __halves2half2(__low2half(o), __high2half(h[L::opp(l)]));
+    }
+    Pack<TS, 2> a;
+    a.v[0] = __low2half(o);
+    a.v[1] = __high2half(o);
+    gstore<TS, 2>(p.push[l] + cell, a);
+    if constexpr (L::ck(0, l) == 1 && (XC & 2)) {
+      if (p.peer_hi[l]) gstore<TS, 2>(p.peer_hi[l] + cell, a);
+    } else if constexpr (L::ck(0, l) == -1 && (XC & 1)) {
+      if (p.peer_lo[l]) gstore<TS, 2>(p.peer_lo[l] + cell, a);
+    }
+  XLBN_END
+}
+
 // ---- half2-state pair path (FP32FP16, BGK): two cells per thread, populations kept as the loaded half2 words ---------------
 // The q post-stream populations of the two cells stay in q 32-bit registers (half2) — the storage format IS the register
 // format — and are widened to a fp32x2 pair on the fly twice: once to accumulate rho and u, once for equilibrium +
@@ -521,66 +605,55 @@ XLBN_DEV void step_body_h2(const StepParams<__half>& p, const int x, const int y
   const bool any_bc = (ids.v[0] != 0) | (ids.v[1] != 0);
   if ((ids.v[0] == 255) & (ids.v[1] == 255)) return;
 
-  __half2 h[Q];
-  XLBN_FOR(Q, l)
-    constexpr int cx = L::ck(0, l), cy = L::ck(1, l), cz = L::ck(2, l);
-    constexpr int tab = (cx == 1 && (XC & 1)) ? 1 : ((cx == -1 && (XC & 2)) ? 2 : 0);
-    const TS* base = p.pull[tab][l];
-    const unsigned row = (cy == 1 ? row_m : (cy == -1 ? row_p : row_c));
-    const Pack<TS, 2> a = gload<TS, 2>(base + (row + (unsigned)z0));
-    if constexpr (cz == 0) {
-      h[l] = __halves2half2(a.v[0], a.v[1]);
-    } else if constexpr (cz == 1) {  // out[z] = in[z - 1]
-      const Pack<TS, 1> e = gload<TS, 1>(base + (row + z_lo));
-      h[l] = __halves2half2(e.v[0], a.v[0]);
-    } else {  // out[z] = in[z + 1]
-      const Pack<TS, 1> e = gload<TS, 1>(base + (row + z_hi));
-      h[l] = __halves2half2(a.v[1], e.v[0]);
-    }
-  XLBN_END
-
-  if (!any_bc) {
-    // moments (macroscopic.py:43-47) over the widened pairs
-    f32x2 rho(0.0f), u[L::D];
-    XLBN_FOR(L::D, d) u[d] = f32x2(0.0f); XLBN_END
+  // Three separate code paths, each with its own load phase, so that the register allocation of the straight-line path
+  // is independent of the boundary code (the branch is taken BEFORE anything is loaded).
+  auto load_all = [&](__half2 (&h)[Q]) {
     XLBN_FOR(Q, l)
-      const f32x2 f(__half22float2(h[l]));
-      rho += f;
-      XLBN_FOR(L::D, d)
-        if constexpr (L::c(d, l) == 1) u[d] += f;
-        else if constexpr (L::c(d, l) == -1) u[d] -= f;
-      XLBN_END
-    XLBN_END
-    const f32x2 inv = rcp_(rho);
-    XLBN_FOR(L::D, d) u[d] = u[d] * inv; XLBN_END
-    f32x2 uu = u[0] * u[0];
-    XLBN_FOR(L::D - 1, d) uu = fma_(u[d + 1], u[d + 1], uu); XLBN_END
-    const f32x2 usqr = f32x2(1.5f) * uu;
-    const f32x2 omega((float)p.omega);
-    // equilibrium + BGK relaxation per population (quadratic_equilibrium.py:35-60, bgk.py:30-34), narrowed and stored at once
-    XLBN_FOR(Q, l)
-      const f32x2 f(__half22float2(h[l]));
-      f32x2 cu(0.0f);
-      XLBN_FOR(L::D, d)
-        if constexpr (L::c(d, l) == 1) cu += u[d];
-        else if constexpr (L::c(d, l) == -1) cu -= u[d];
-      XLBN_END
-      cu *= f32x2(3.0f);
-      const f32x2 feq = rho * f32x2(L::w(l)) * (fma_(cu, fma_(f32x2(0.5f), cu, f32x2(1.0f)), f32x2(1.0f)) - usqr);
-      const f32x2 out = fma_(-omega, f - feq, f);
-      const __half2 o = __float22half2_rn(out.v);
-      Pack<TS, 2> a;
-      a.v[0] = __low2half(o);
-      a.v[1] = __high2half(o);
-      gstore<TS, 2>(p.push[l] + cell, a);
-      if constexpr (L::ck(0, l) == 1 && (XC & 2)) {
-        if (p.peer_hi[l]) gstore<TS, 2>(p.peer_hi[l] + cell, a);
-      } else if constexpr (L::ck(0, l) == -1 && (XC & 1)) {
-        if (p.peer_lo[l]) gstore<TS, 2>(p.peer_lo[l] + cell, a);
+      constexpr int cx = L::ck(0, l), cy = L::ck(1, l), cz = L::ck(2, l);
+      constexpr int tab = (cx == 1 && (XC & 1)) ? 1 : ((cx == -1 && (XC & 2)) ? 2 : 0);
+      const TS* base = p.pull[tab][l];
+      const unsigned row = (cy == 1 ? row_m : (cy == -1 ? row_p : row_c));
+      const Pack<TS, 2> a = gload<TS, 2>(base + (row + (unsigned)z0));
+      if constexpr (cz == 0) {
+        h[l] = __halves2half2(a.v[0], a.v[1]);
+      } else if constexpr (cz == 1) {  // out[z] = in[z - 1]
+        const Pack<TS, 1> e = gload<TS, 1>(base + (row + z_lo));
+        h[l] = __halves2half2(e.v[0], a.v[0]);
+      } else {  // out[z] = in[z + 1]
+        const Pack<TS, 1> e = gload<TS, 1>(base + (row + z_hi));
+        h[l] = __halves2half2(a.v[1], e.v[0]);
       }
     XLBN_END
+  };
+
+  // Warp-uniform choice of the code path (threads of a warp never serialise through two paths):
+  //   no boundary cell in the warp                      -> straight pair path
+  //   only fluid / FullwayBounceBack / EquilibriumBC    -> pair path with per-half boundary handling
+  //   anything else (other BC kinds, solid cells)       -> per-thread: pair path or scalar boundary tail
+  const int k0 = ids.v[0] ? (int)p.kinds[ids.v[0]] : 0, k1 = ids.v[1] ? (int)p.kinds[ids.v[1]] : 0;
+  const auto simple = [](int id, int k) { return id != 255 && (k == XLBN_BC_NONE || k == XLBN_BC_FULLWAY_BOUNCE_BACK || k == XLBN_BC_EQUILIBRIUM); };
+  const unsigned active = __activemask();
+  const bool warp_any_bc = __any_sync(active, any_bc);
+  if (!warp_any_bc) {
+    __half2 h[Q];
+    load_all(h);
+    h2_collide_store<L, XC, false>(p, h, cell, 0, 0);
     return;
   }
+  if (__all_sync(active, simple(ids.v[0], k0) && simple(ids.v[1], k1))) {
+    __half2 h[Q];
+    load_all(h);
+    h2_collide_store<L, XC, true>(p, h, cell, ids.v[0], ids.v[1]);
+    return;
+  }
+  if (!any_bc) {
+    __half2 h[Q];
+    load_all(h);
+    h2_collide_store<L, XC, false>(p, h, cell, 0, 0);
+    return;
+  }
+  __half2 h[Q];
+  load_all(h);
   // threads with boundary cells: widen and take the scalar boundary tail
   float fs[V][Q];
   XLBN_FOR(Q, l)
@@ -656,7 +729,7 @@ inline int pick_cells_per_thread(int requested, int dflt, int esize, int nz, con
 // half2 registers and are converted on the fly, once for the moments and once for the relaxation).
 template <class L, int COLL, class TC, class TS>
 int launch_step(const StepParams<TS>& p, int x_count, int requested_v, const void* f0, const void* f1, const void* g0, const void* g1,
-                const void* o0, const void* o1, cudaStream_t stream) {
+                const void* o0, const void* o1, BcEntry* table_rw, double* eq_omega_state, cudaStream_t stream) {
   constexpr bool can_pack = sizeof(TC) == 4 && sizeof(TS) <= 4;
   // defaults selected on B200 (profiles/)
   int req = requested_v;
@@ -664,7 +737,16 @@ int launch_step(const StepParams<TS>& p, int x_count, int requested_v, const voi
   if (req == 0) req = can_h2 ? 202 : 1;
   if (req == 202) {
     if constexpr (can_h2) {
-      if (pick_cells_per_thread(2, 1, (int)sizeof(TS), p.nz, p.bc, {f0, f1, g0, g1, o0, o1}) == 2) return launch_step_v<L, COLL, TC, TS, 2, 2>(p, x_count, stream);
+      if (pick_cells_per_thread(2, 1, (int)sizeof(TS), p.nz, p.bc, {f0, f1, g0, g1, o0, o1}) == 2) {
+        if (eq_omega_state && !(p.omega == *eq_omega_state)) {
+          // rare (first step / omega changed): recompute the EquilibriumBC constants before any reader can run
+          bc_precompute_kernel<L, COLL><<<1, 256, 0, stream>>>(table_rw, (float)p.omega);
+          XLBN_LAUNCH_OK("bc_precompute_kernel");
+          XLBN_CUDA_OK(cudaStreamSynchronize(stream));
+          *eq_omega_state = p.omega;
+        }
+        return launch_step_v<L, COLL, TC, TS, 2, 2>(p, x_count, stream);
+      }
       req = 1;  // odd nz or misaligned arrays: scalar fallback
     } else {
       return fail(XLBN_E_ARG, "cells_per_thread = 202: the half2-state path exists for FP32FP16 BGK only");
@@ -694,6 +776,8 @@ struct StepCall {
   const uint8_t* bc;
   const uint32_t* miss;
   const BcEntry* table;
+  BcEntry* table_rw;        // same table, writable (EquilibriumBC constants)
+  double* eq_omega_state;  // host: omega the EquilibriumBC constants were computed for; NULL = stepper has no EquilibriumBC
   const uint8_t* kinds;  // host, 256 entries
   int nx, ny, nz, x_begin, x_count;
   double omega;
@@ -752,7 +836,7 @@ int run_step_typed(const StepCall& c) {
   p.plane = plane;
   p.n = n;
   p.omega = c.omega;
-  return launch_step<L, COLL, TC, TS>(p, c.x_count, c.requested_v, c.f0, c.f1, c.ghost_lo, c.ghost_hi, c.out_lo, c.out_hi, c.stream);
+  return launch_step<L, COLL, TC, TS>(p, c.x_count, c.requested_v, c.f0, c.f1, c.ghost_lo, c.ghost_hi, c.out_lo, c.out_hi, c.table_rw, c.eq_omega_state, c.stream);
 }
 
 #define XLBN_DEFINE_STEP_DISPATCH(LAT, COLL)                                                                      \
