@@ -158,3 +158,21 @@ def test_c3_sphere_d3q27_kbc_256x64x64_against_c_oracle(v):
     assert np.array_equal(bm, bc_mask) and np.array_equal(mm, missing)
     assert np.isfinite(f).all()
     assert rel_err(f, ref) <= 1e-5, rel_err(f, ref)
+
+
+@pytest.mark.parametrize("policy", ["FP32FP32", "FP32FP16"])
+@pytest.mark.parametrize("shape", [(10, 9, 7), (6, 5, 9)])
+def test_odd_extents_fall_back_to_one_cell_per_thread(policy, shape):
+    """Odd nz cannot use the vector / pair variants: the library falls back to the one-cell path and stays correct."""
+    from oracle import lbm_numpy as O
+
+    lat = O.Lattice("D3Q19")
+    rng = np.random.default_rng(5)
+    cdt, sdt = O.policy_dtypes(policy)
+    f_init = O.initialize_eq(shape, lat, policy, rho=1 + 1e-2 * rng.standard_normal((1,) + shape), u=1e-2 * rng.standard_normal((3,) + shape))
+    g = load_golden("periodic_d3q19_bgk_fp32")
+    g.update(shape=shape, steps=10, omega=1.4, policy=policy, f_init=f_init, bcs=[], n_bc=0)
+    ref, _, _ = oracle_run(g)
+    for v in (0, 2, 4, 202 if policy == "FP32FP16" else 102):
+        f, _, _ = native_run(g, cells_per_thread=v)
+        assert rel_err(f, ref) <= RTOL[policy]
