@@ -1,4 +1,5 @@
-from xlb_b200.grid.grid import grid_factory as grid_factory
-from xlb_b200.grid.grid import Grid, WarpGrid, JaxGrid
+"""Grid namespace: one slab-aware Grid class; WarpGrid / JaxGrid only select the field-shape convention."""
 
-__all__ = ["grid_factory", "Grid", "WarpGrid", "JaxGrid"]
+from xlb_b200._exports import export
+
+export(globals(), __name__, {"grid": ["grid_factory", "Grid", "WarpGrid", "JaxGrid"]})

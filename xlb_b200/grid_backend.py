@@ -1,9 +1,5 @@
-"""Grid-backend enum kept for import compatibility (reference: xlb/grid_backend.py)."""
+"""Kept so that `from xlb.grid_backend import GridBackend` keeps working; the framework has a single grid type."""
 
-from enum import Enum, auto
+from enum import Enum
 
-
-class GridBackend(Enum):
-    JAX = auto()
-    WARP = auto()
-    OOC = auto()
+GridBackend = Enum("GridBackend", ["JAX", "WARP", "OOC"])

@@ -1,2 +1,5 @@
-from xlb_b200.operator.operator import Operator
-from xlb_b200.operator.parallel_operator import ParallelOperator
+"""Operator base class and the x-slab wrapper (namespace of reference xlb/operator)."""
+
+from xlb_b200._exports import export
+
+export(globals(), __name__, {"operator": ["Operator"], "parallel_operator": ["ParallelOperator"]})

@@ -1,10 +1,20 @@
-from xlb_b200.operator.boundary_condition.helper_functions_bc import HelperFunctionsBC
-from xlb_b200.operator.boundary_condition.boundary_condition import BoundaryCondition, ImplementationStep
-from xlb_b200.operator.boundary_condition.boundary_condition_registry import BoundaryConditionRegistry
-from xlb_b200.operator.boundary_condition.bc_equilibrium import EquilibriumBC
-from xlb_b200.operator.boundary_condition.bc_do_nothing import DoNothingBC
-from xlb_b200.operator.boundary_condition.bc_halfway_bounce_back import HalfwayBounceBackBC
-from xlb_b200.operator.boundary_condition.bc_fullway_bounce_back import FullwayBounceBackBC
-from xlb_b200.operator.boundary_condition.bc_zouhe import ZouHeBC
-from xlb_b200.operator.boundary_condition.bc_regularized import RegularizedBC
-from xlb_b200.operator.boundary_condition.bc_extrapolation_outflow import ExtrapolationOutflowBC
+"""Boundary conditions (namespace of reference xlb/operator/boundary_condition; GradsApproximationBC is out of scope)."""
+
+from xlb_b200._exports import export
+
+export(
+    globals(),
+    __name__,
+    {
+        "helper_functions_bc": ["HelperFunctionsBC"],
+        "boundary_condition": ["BoundaryCondition", "ImplementationStep"],
+        "boundary_condition_registry": ["BoundaryConditionRegistry"],
+        "bc_equilibrium": ["EquilibriumBC"],
+        "bc_do_nothing": ["DoNothingBC"],
+        "bc_halfway_bounce_back": ["HalfwayBounceBackBC"],
+        "bc_fullway_bounce_back": ["FullwayBounceBackBC"],
+        "bc_zouhe": ["ZouHeBC"],
+        "bc_regularized": ["RegularizedBC"],
+        "bc_extrapolation_outflow": ["ExtrapolationOutflowBC"],
+    },
+)

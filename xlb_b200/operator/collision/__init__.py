@@ -1,3 +1,5 @@
-from xlb_b200.operator.collision.collision import Collision
-from xlb_b200.operator.collision.bgk import BGK
-from xlb_b200.operator.collision.kbc import KBC
+"""Collision operators in scope: BGK and KBC (ForcedCollision / SmagorinskyLESBGK are not)."""
+
+from xlb_b200._exports import export
+
+export(globals(), __name__, {"collision": ["Collision"], "bgk": ["BGK"], "kbc": ["KBC"]})

@@ -1,2 +1,5 @@
-from xlb_b200.operator.equilibrium.equilibrium import Equilibrium
-from xlb_b200.operator.equilibrium.quadratic_equilibrium import QuadraticEquilibrium
+"""Equilibrium operators."""
+
+from xlb_b200._exports import export
+
+export(globals(), __name__, {"equilibrium": ["Equilibrium"], "quadratic_equilibrium": ["QuadraticEquilibrium"]})

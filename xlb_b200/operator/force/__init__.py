@@ -1,1 +1,5 @@
-from xlb_b200.operator.force.momentum_transfer import MomentumTransfer
+"""Force evaluation: momentum exchange on a no-slip boundary."""
+
+from xlb_b200._exports import export
+
+export(globals(), __name__, {"momentum_transfer": ["MomentumTransfer"]})

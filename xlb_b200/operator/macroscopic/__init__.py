@@ -1,4 +1,5 @@
-from xlb_b200.operator.macroscopic.macroscopic import Macroscopic
-from xlb_b200.operator.macroscopic.second_moment import SecondMoment
-from xlb_b200.operator.macroscopic.zero_moment import ZeroMoment
-from xlb_b200.operator.macroscopic.first_moment import FirstMoment
+"""Moments of the populations: density, velocity, momentum flux."""
+
+from xlb_b200._exports import export
+
+export(globals(), __name__, {"macroscopic": ["Macroscopic"], "second_moment": ["SecondMoment"], "zero_moment": ["ZeroMoment"], "first_moment": ["FirstMoment"]})

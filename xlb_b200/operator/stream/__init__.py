@@ -1,1 +1,5 @@
-from xlb_b200.operator.stream.stream import Stream
+"""Streaming operator namespace."""
+
+from xlb_b200._exports import export
+
+export(globals(), __name__, {"stream": ["Stream"]})
