@@ -63,7 +63,7 @@ def _worker(rank, world, port, lattice, out):
 @pytest.mark.parametrize("lattice", ["D3Q19", "D3Q27"])
 def test_ring_exchange_world_size_2(lattice):
     world = 2
-    with mp.Manager() as manager:
+    with mp.get_context("spawn").Manager() as manager:  # never fork a multi-threaded (torch) process
         out = manager.dict()
         mp.spawn(_worker, args=(world, _free_port(), lattice, out), nprocs=world, join=True)
         assert all(all(out[r]) for r in range(world)), dict(out)
