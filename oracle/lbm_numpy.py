@@ -499,7 +499,16 @@ def bounding_box_indices(shape, remove_edges=False):
 # --------------------------------------------------------------------------------------------
 
 
-def step(f0, bc_mask, missing, bcs: Sequence[BC], omega, lat: Lattice, policy="FP32FP32", collision="BGK", flavor="jax", f1_prev=None):
+def exact_difference_force(f_post_collision, feq, rho, u, force, lat: Lattice):
+    """ExactDifference body force: f += feq(rho, u + F) - feq(rho, u)  (force/exact_difference_force.py:45-70;
+    applied after the collision by ForcedCollision, collision/forced_collision.py:34-39).  Not built in xlb_b200 yet
+    (SURVEY.md §8f N4): the oracle and its golden vector are the target for the next round."""
+    dt = u.dtype
+    delta_u = np.asarray(force, dtype=dt).reshape((lat.d,) + (1,) * lat.d)
+    return f_post_collision + (equilibrium(rho, u + delta_u, lat) - feq)
+
+
+def step(f0, bc_mask, missing, bcs: Sequence[BC], omega, lat: Lattice, policy="FP32FP32", collision="BGK", flavor="jax", f1_prev=None, force=None):
     """One pull step.  Returns f1 in the store dtype.
 
     flavor="warp" adds the two observable Warp-only behaviours: cells with bc_mask == 255 are skipped entirely
@@ -519,6 +528,8 @@ def step(f0, bc_mask, missing, bcs: Sequence[BC], omega, lat: Lattice, policy="F
             f_out = collide_kbc(f_post, feq, rho, lat, omega)
     else:
         raise ValueError(collision)
+    if force is not None:
+        f_out = exact_difference_force(f_out, feq, rho, u, force, lat)
     for bc in bcs:  # L179-187
         if bc.kind == "outflow":
             f_out = outflow_update_aux(bc, f_post, f_out, bc_mask, missing, lat)
@@ -531,11 +542,11 @@ def step(f0, bc_mask, missing, bcs: Sequence[BC], omega, lat: Lattice, policy="F
     return f1
 
 
-def run(f0, bc_mask, missing, bcs, omega, lat, nsteps, policy="FP32FP32", collision="BGK", flavor="jax"):
+def run(f0, bc_mask, missing, bcs, omega, lat, nsteps, policy="FP32FP32", collision="BGK", flavor="jax", force=None):
     """The user loop of examples/performance/mlups_3d.py:77-80: step then swap."""
     f_a, f_b = f0, f0.copy()
     for _ in range(nsteps):
-        f_b = step(f_a, bc_mask, missing, bcs, omega, lat, policy, collision, flavor, f1_prev=f_b)
+        f_b = step(f_a, bc_mask, missing, bcs, omega, lat, policy, collision, flavor, f1_prev=f_b, force=force)
         f_a, f_b = f_b, f_a
     return f_a
 

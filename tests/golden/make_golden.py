@@ -169,7 +169,7 @@ def sphere(name, lattice, policy, shape, steps, collision, omega=1.6, outlet="ou
     run_and_save(name, dict(lattice=lattice, policy=policy, collision=collision, shape=np.array(shape)), stepper, meta, steps, omega, force_bc=bc_sph)
 
 
-def periodic(name, lattice, policy, shape, steps, collision, omega):
+def periodic(name, lattice, policy, shape, steps, collision, omega, force=None):
     """Fully periodic box from a seeded random velocity field (as examples/cfd/turbulent_channel_3d.py:130-135 seeds u)."""
     vs, pp = init(lattice, policy)
     grid = grid_factory(shape)
@@ -181,8 +181,12 @@ def periodic(name, lattice, policy, shape, steps, collision, omega):
         f = initialize_eq(None, grid, velocity_set, precision_policy, compute_backend, rho=jnp.array(rho0), u=jnp.array(u0))
         return precision_policy.cast_to_store_jax(f)
 
-    stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=[], collision_type=collision)
-    run_and_save(name, dict(lattice=lattice, policy=policy, collision=collision, shape=np.array(shape), rho0=rho0, u0=u0), stepper, [], steps, omega, initializer)
+    kw = {} if force is None else dict(force_vector=jnp.array(force, dtype=pp.compute_precision.jax_dtype))
+    stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=[], collision_type=collision, **kw)
+    meta = dict(lattice=lattice, policy=policy, collision=collision, shape=np.array(shape), rho0=rho0, u0=u0)
+    if force is not None:
+        meta["force_vector"] = np.asarray(force, dtype=np.float64)
+    run_and_save(name, meta, stepper, [], steps, omega, initializer)
 
 
 def operator_vectors():
@@ -229,3 +233,5 @@ if __name__ == "__main__":
     sphere("sphere_d3q19_bgk_donothing_fp32", "D3Q19", "FP32FP32", (32, 14, 14), 30, "BGK", omega=1.2, outlet="donothing")
     periodic("periodic_d3q19_bgk_fp32", "D3Q19", "FP32FP32", (12, 10, 8), 30, "BGK", 1.5)
     periodic("periodic_d3q27_kbc_fp32", "D3Q27", "FP32FP32", (12, 10, 8), 30, "KBC", 1.8)
+    # body force (ForcedCollision + ExactDifference, as examples/cfd/turbulent_channel_3d.py drives its channel): target for round 2
+    periodic("periodic_d3q19_bgk_forced_fp32", "D3Q19", "FP32FP32", (12, 10, 8), 30, "BGK", 1.5, force=(1e-5, 0.0, 0.0))

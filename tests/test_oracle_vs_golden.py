@@ -65,3 +65,16 @@ def test_momentum_transfer_vectors(name):
     bc = oracle_bcs(g)[int(g["force_bc"])]
     force = O.momentum_transfer(bc, g["f_final"].astype(cdt), g["bc_mask"], unpack_bits(g["missing_bits"], lat.q), lat)
     assert np.allclose(force, g["force"], rtol=1e-6, atol=1e-9)
+
+
+def test_forced_collision_vector():
+    """ForcedCollision + ExactDifference (collision/forced_collision.py:34-39, force/exact_difference_force.py:45-70):
+    oracle vs the reference's own run.  The CUDA path does not implement body forces yet."""
+    g = load_golden("periodic_d3q19_bgk_forced_fp32")
+    lat = O.Lattice(g["lattice"])
+    bm = np.zeros((1,) + g["shape"], np.uint8)
+    mm = np.zeros((lat.q,) + g["shape"], bool)
+    f = O.run(g["f_init"].copy(), bm, mm, [], g["omega"], lat, g["steps"], policy=g["policy"], collision=g["collision"], force=g["force_vector"])
+    assert rel_err(f, g["f_final"]) <= 1e-7
+    unforced = O.run(g["f_init"].copy(), bm, mm, [], g["omega"], lat, g["steps"], policy=g["policy"], collision=g["collision"])
+    assert rel_err(unforced, g["f_final"]) > 1e-6  # the force does something

@@ -96,6 +96,19 @@ class PeerHalo:
         except Exception:
             pass
 
+    def timed_out(self) -> bool:
+        """True if a device-side wait for the neighbours' step counters ever gave up (10 s; the wait kernel then sets a
+        marker instead of hanging the GPU).  Synchronises the device; call it outside the stepping loop."""
+        base, nbytes = C.c_void_p(), C.c_longlong()
+        native.check(native.lib().xlbn_halo_ghost_ptr(self.handle, C.byref(base), C.byref(nbytes)))
+
+        class _Flags:  # the last 256 bytes of the ghost block hold int flags[4]; flags[2] is the timeout marker
+            __cuda_array_interface__ = {"shape": (4,), "typestr": "<i4", "data": (base.value + nbytes.value - 256, True), "version": 2}
+
+        torch.cuda.synchronize(self.device)
+        flags = torch.as_tensor(_Flags(), device=self.device).cpu()
+        return bool(flags[2].item() != 0)
+
     def step(self, stepper_handle, f_0, f_1, bc_mask, bits, dims, omega, t):
         L = native.lib()
         nx, ny, nz = dims
