@@ -21,6 +21,12 @@ STEP_CASES = [
     "periodic_d3q19_bgk_fp32",
     "periodic_d3q27_kbc_fp32",
 ]
+# Cases added after the round-1 GPU budget was spent: pinned against the reference on the CPU (both oracles); the CUDA path
+# sees them for the first time in tests/test_zz_first_run_gpu.py.  2-D channel past a cylinder with the non-trivial BCs.
+# (A KBC variant of this channel is deliberately absent: with a Regularized inlet the non-equilibrium part vanishes there,
+# gamma = <dh|ds>/(eps + <dh|dh>) becomes 0/0-like and the run is ill-conditioned — the numpy oracle in fp32 and in fp64
+# differ by 2e-3 after 60 steps — so it cannot pin anything.)
+EXTRA_CASES_2D = ["channel2d_d2q9_bgk_outflow_fp32", "channel2d_d2q9_bgk_zouhe_pressure_fp32"]
 # relative tolerance (max |a-b| / max |b|) per store/compute policy; north-star: 1e-5 fp32, 1e-3 fp16 storage
 RTOL = {"FP32FP32": 1e-5, "FP64FP32": 1e-5, "FP64FP64": 1e-9, "FP32FP16": 1e-3, "FP64FP16": 1e-3}
 

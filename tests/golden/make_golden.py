@@ -169,6 +169,46 @@ def sphere(name, lattice, policy, shape, steps, collision, omega=1.6, outlet="ou
     run_and_save(name, dict(lattice=lattice, policy=policy, collision=collision, shape=np.array(shape)), stepper, meta, steps, omega, force_bc=bc_sph)
 
 
+def channel2d(name, policy, shape, steps, collision, omega, outlet="outflow", inlet="regularized"):
+    """2-D channel past a cylinder (D2Q9): Fullway walls, parabolic velocity inlet, outlet, Halfway cylinder — the 2-D
+    counterpart of the sphere case (same BC classes as examples/cfd/flow_past_sphere_3d.py)."""
+    vs, pp = init("D2Q9", policy)
+    grid = grid_factory(shape)
+    box, bne = grid.bounding_box_indices(), grid.bounding_box_indices(remove_edges=True)
+    inlet_idx, outlet_idx = bne["left"], bne["right"]
+    walls = [box["bottom"][i] + box["top"][i] for i in range(2)]
+    walls = np.unique(np.array(walls), axis=-1).tolist()
+    X, Y = np.meshgrid(np.arange(shape[0]), np.arange(shape[1]), indexing="ij")
+    ind = np.where((X - shape[0] // 5) ** 2 + (Y - shape[1] // 2) ** 2 < (shape[1] // 6) ** 2)
+    cyl = [tuple(ind[i]) for i in range(2)]
+    H = float(shape[1] - 1)
+
+    def profile():
+        y = jnp.arange(shape[1])
+        ux = 0.04 * jnp.maximum(0.0, 1.0 - (2.0 * (y - H / 2.0) / H) ** 2.0)
+        return jnp.stack([ux, jnp.zeros_like(ux)])
+
+    bc_walls = FullwayBounceBackBC(indices=walls)
+    In = RegularizedBC if inlet == "regularized" else ZouHeBC
+    bc_in = In("velocity", profile=profile, indices=inlet_idx)
+    if outlet == "outflow":
+        bc_out, out_meta = ExtrapolationOutflowBC(indices=outlet_idx), dict(kind="outflow")
+    else:
+        bc_out = ZouHeBC("pressure", prescribed_value=1.0, indices=outlet_idx)
+        out_meta = dict(kind="zouhe", bc_type="pressure", prescribed=np.float64(1.0))
+    bc_cyl = HalfwayBounceBackBC(indices=cyl)
+    bcs = [bc_walls, bc_in, bc_out, bc_cyl]
+    stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=bcs, collision_type=collision)
+    out_meta.update(id=bc_out.id, indices=np.array(outlet_idx))
+    meta = [
+        dict(kind="fullway", id=bc_walls.id, indices=np.array(walls)),
+        dict(kind=inlet, id=bc_in.id, indices=np.array(inlet_idx), bc_type="velocity", prescribed=np.asarray(profile())),
+        out_meta,
+        dict(kind="halfway", id=bc_cyl.id, indices=np.array(cyl)),
+    ]
+    run_and_save(name, dict(lattice="D2Q9", policy=policy, collision=collision, shape=np.array(shape)), stepper, meta, steps, omega, force_bc=bc_cyl)
+
+
 def periodic(name, lattice, policy, shape, steps, collision, omega, force=None):
     """Fully periodic box from a seeded random velocity field (as examples/cfd/turbulent_channel_3d.py:130-135 seeds u)."""
     vs, pp = init(lattice, policy)
@@ -233,5 +273,7 @@ if __name__ == "__main__":
     sphere("sphere_d3q19_bgk_donothing_fp32", "D3Q19", "FP32FP32", (32, 14, 14), 30, "BGK", omega=1.2, outlet="donothing")
     periodic("periodic_d3q19_bgk_fp32", "D3Q19", "FP32FP32", (12, 10, 8), 30, "BGK", 1.5)
     periodic("periodic_d3q27_kbc_fp32", "D3Q27", "FP32FP32", (12, 10, 8), 30, "KBC", 1.8)
+    channel2d("channel2d_d2q9_bgk_outflow_fp32", "FP32FP32", (60, 24), 60, "BGK", 1.6)
+    channel2d("channel2d_d2q9_bgk_zouhe_pressure_fp32", "FP32FP32", (60, 24), 60, "BGK", 1.5, outlet="pressure", inlet="zouhe")
     # body force (ForcedCollision + ExactDifference, as examples/cfd/turbulent_channel_3d.py drives its channel): target for round 2
     periodic("periodic_d3q19_bgk_forced_fp32", "D3Q19", "FP32FP32", (12, 10, 8), 30, "BGK", 1.5, force=(1e-5, 0.0, 0.0))
