@@ -39,8 +39,11 @@ enum xlbn_lattice { XLBN_D2Q9 = 0, XLBN_D3Q19 = 1, XLBN_D3Q27 = 2 };
 /* array element types (reference: xlb/precision_policy.py:8-43) */
 enum xlbn_dtype { XLBN_F16 = 0, XLBN_F32 = 1, XLBN_F64 = 2, XLBN_U8 = 3, XLBN_BOOL = 4 };
 
-/* collision operators (reference: xlb/operator/collision/bgk.py:17-34, kbc.py:40-100) */
-enum xlbn_collision { XLBN_BGK = 0, XLBN_KBC = 1 };
+/* collision operators (reference: xlb/operator/collision/bgk.py:17-34, kbc.py:40-100, smagorinsky_les_bgk.py:37-90).
+ * XLBN_COLLISION_FORCED is a FLAG or-ed onto a base operator: ForcedCollision with the ExactDifference forcing scheme
+ * (collision/forced_collision.py:34-39, force/exact_difference_force.py:45-85).  Steppers get it through
+ * xlbn_stepper_set_force; the stand-alone xlbn_collide_ext takes it in `collision`. */
+enum xlbn_collision { XLBN_BGK = 0, XLBN_KBC = 1, XLBN_SMAGORINSKY_LES_BGK = 2, XLBN_COLLISION_FORCED = 4 };
 
 /* boundary-condition kinds (reference: xlb/operator/boundary_condition/bc_*.py) */
 enum xlbn_bc_kind {
@@ -119,6 +122,12 @@ int xlbn_lattice_tables(int lattice, int32_t* c, double* w, int32_t* opp);
 /* Replaces: IncompressibleNavierStokesStepper._construct_warp (closure-specialised kernel, nse_stepper.py:245-383). */
 int xlbn_stepper_create(const xlbn_stepper_desc* desc, xlbn_stepper** out);
 int xlbn_stepper_destroy(xlbn_stepper* s);
+/* Constant body force: the stepper's collision becomes ForcedCollision(collision, "exact_difference", force)
+ * (nse_stepper.py:45-46; forced_collision.py:34-39: f_out += feq(rho, u + force) - feq(rho, u) after the collision, on
+ * every cell that collides).  force: host double[3] (2-D lattices read the first two), NULL removes the force. */
+int xlbn_stepper_set_force(xlbn_stepper* s, const double* force);
+/* Smagorinsky coefficient of an XLBN_SMAGORINSKY_LES_BGK stepper (smagorinsky_les_bgk.py:24; default 0.17). */
+int xlbn_stepper_set_smagorinsky(xlbn_stepper* s, double coefficient);
 
 /* One time step.  Replaces the launch in IncompressibleNavierStokesStepper.warp_implementation
  * (nse_stepper.py:385-392; kernel body 344-381) and the jitted jax_implementation_pull (147-192).
@@ -177,6 +186,16 @@ int xlbn_second_moment(int lattice, int compute_dtype, const void* f, int f_dtyp
 int xlbn_collide(int lattice, int collision, int compute_dtype, const void* f, int f_dtype, const void* feq, int feq_dtype,
                  void* fout, int fout_dtype, const void* rho, int rho_dtype, double omega, const int32_t dims[3],
                  void* stream);
+/* Any collision operator incl. SmagorinskyLESBGK and the ForcedCollision wrapper (smagorinsky_les_bgk.py:92-138,
+ * forced_collision.py:41-103).  collision = base | XLBN_COLLISION_FORCED; rho is read by KBC and by the forcing, u
+ * ([d][...]) by the forcing only; force: host double[3] or NULL. */
+int xlbn_collide_ext(int lattice, int collision, int compute_dtype, const void* f, int f_dtype, const void* feq, int feq_dtype,
+                     void* fout, int fout_dtype, const void* rho, int rho_dtype, const void* u, int u_dtype, double omega,
+                     const double* force, double smagorinsky, const int32_t dims[3], void* stream);
+/* ExactDifference stand-alone (exact_difference_force.py:87-125): fout = f_postcollision + feq(rho, u + force) - feq. */
+int xlbn_exact_difference(int lattice, int compute_dtype, const void* f_postcollision, int f_dtype, const void* feq, int feq_dtype,
+                          void* fout, int fout_dtype, const void* rho, int rho_dtype, const void* u, int u_dtype,
+                          const double* force, const int32_t dims[3], void* stream);
 /* Generic stand-alone BC kernel (boundary_condition.py:83-117): cells with bc_mask == bc.id get the BC's functional,
  * all others keep f_post.  `missing` is the reference's bool [q][...] array. f_pre / f_post share `dtype`. */
 int xlbn_bc_apply(int lattice, int compute_dtype, const xlbn_bc_desc* bc, const void* f_pre, void* f_post, int dtype,

@@ -25,6 +25,7 @@ class LbmDesc(C.Structure):
         ("d", C.c_int), ("q", C.c_int), ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("collision", C.c_int), ("compute", C.c_int),
         ("store", C.c_int), ("omega", C.c_double), ("c", C.c_int * 81), ("opp", C.c_int * 27), ("w", C.c_double * 27), ("cc", C.c_double * 162),
         ("qi", C.c_double * 162), ("bc_kind", C.c_int * 256), ("bc_rho", C.c_double * 256), ("bc_u", C.c_double * 768),
+        ("has_force", C.c_int), ("force", C.c_double * 3), ("smagorinsky", C.c_double),
     ]  # fmt: skip
 
 
@@ -39,13 +40,17 @@ def _lib():
     return lib
 
 
-def make_desc(lat: O.Lattice, shape, policy, collision, omega, bcs):
+def make_desc(lat: O.Lattice, shape, policy, collision, omega, bcs, force=None, smagorinsky=0.17):
     cdt, sdt = O.policy_dtypes(policy)
     d = LbmDesc()
     d.d, d.q = lat.d, lat.q
     sh = tuple(shape) + (1,) * (3 - len(shape))
     d.nx, d.ny, d.nz = sh
-    d.collision = {"BGK": 0, "KBC": 1}[collision]
+    d.collision = {"BGK": 0, "KBC": 1, "SmagorinskyLESBGK": 2}[collision]
+    d.smagorinsky = float(smagorinsky)
+    d.has_force = int(force is not None)
+    for a in range(lat.d if force is not None else 0):
+        d.force[a] = float(force[a])
     d.compute = 1 if cdt == np.float32 else 2
     d.store = _STORE[np.dtype(sdt)]
     d.omega = float(omega)
@@ -82,14 +87,14 @@ def write_aux(f1, bcs, bc_mask, missing, lat, policy):
         f1[(0,) + cells] = val.astype(f1.dtype)
 
 
-def run(f0, bc_mask, missing, bcs, omega, lat, nsteps, policy="FP32FP32", collision="BGK", threads=None):
+def run(f0, bc_mask, missing, bcs, omega, lat, nsteps, policy="FP32FP32", collision="BGK", threads=None, force=None, smagorinsky=0.17):
     """Same contract as oracle.lbm_numpy.run (user loop with buffer swap); returns the final populations."""
     threads = threads or os.cpu_count() or 1
     cdt, sdt = O.policy_dtypes(policy)
     fa = np.ascontiguousarray(f0, dtype=sdt).copy()
     fb = fa.copy()
     write_aux(fb, bcs, bc_mask, missing, lat, policy)
-    d = make_desc(lat, f0.shape[1:], policy, collision, omega, bcs)
+    d = make_desc(lat, f0.shape[1:], policy, collision, omega, bcs, force, smagorinsky)
     bm = np.ascontiguousarray(bc_mask, dtype=np.uint8)
     mm = np.ascontiguousarray(missing).view(np.uint8)
     which = _lib().lbm_ref_run(C.byref(d), fa.ctypes.data, fb.ctypes.data, bm.ctypes.data, mm.ctypes.data, int(nsteps), int(threads))

@@ -177,6 +177,26 @@ def collide_kbc(f, feq, rho, lat: Lattice, omega, epsilon=1e-32):
     return f - beta * (dt(2.0) * delta_s + gamma[None, ...] * delta_h)
 
 
+def collide_smagorinsky(f, feq, lat: Lattice, omega, coef=0.17):
+    """SmagorinskyLESBGK (smagorinsky_les_bgk.py:37-90; the reference has a Warp functional only, and it indexes c[2, l],
+    i.e. 3-D only).  The 'strain' it uses is a weighted sum of squared non-equilibrium POPULATIONS selected by the SIGNED
+    component sum of c_l (== 1: weight 1, >= 2: weight 2), accumulated in l order; restated literally."""
+    if lat.d != 3:
+        raise ValueError("SmagorinskyLESBGK: the reference functional reads c[2, l] (3-D lattices only)")
+    dt = f.dtype.type
+    fneq = f - feq
+    csum = lat.c.sum(axis=0)
+    strain = np.zeros(f.shape[1:], dtype=f.dtype)
+    for l in range(lat.q):
+        if csum[l] == 1:
+            strain = strain + fneq[l] * fneq[l]
+        if csum[l] >= 2:
+            strain = strain + dt(2.0) * fneq[l] * fneq[l]
+    tau0 = dt(1.0) / dt(omega)
+    tau = tau0 + dt(0.5) * (np.sqrt(tau0 * tau0 + dt(36.0) * (dt(coef) ** dt(2.0)) * np.sqrt(strain)) - tau0)
+    return f - (dt(1.0) / tau)[None, ...] * fneq
+
+
 # --------------------------------------------------------------------------------------------
 # Boundary conditions
 # --------------------------------------------------------------------------------------------
@@ -508,7 +528,8 @@ def exact_difference_force(f_post_collision, feq, rho, u, force, lat: Lattice):
     return f_post_collision + (equilibrium(rho, u + delta_u, lat) - feq)
 
 
-def step(f0, bc_mask, missing, bcs: Sequence[BC], omega, lat: Lattice, policy="FP32FP32", collision="BGK", flavor="jax", f1_prev=None, force=None):
+def step(f0, bc_mask, missing, bcs: Sequence[BC], omega, lat: Lattice, policy="FP32FP32", collision="BGK", flavor="jax", f1_prev=None, force=None,
+         smagorinsky=0.17):
     """One pull step.  Returns f1 in the store dtype.
 
     flavor="warp" adds the two observable Warp-only behaviours: cells with bc_mask == 255 are skipped entirely
@@ -526,6 +547,8 @@ def step(f0, bc_mask, missing, bcs: Sequence[BC], omega, lat: Lattice, policy="F
     elif collision == "KBC":
         with np.errstate(all="ignore"):
             f_out = collide_kbc(f_post, feq, rho, lat, omega)
+    elif collision == "SmagorinskyLESBGK":  # nse_stepper.py:42-43
+        f_out = collide_smagorinsky(f_post, feq, lat, omega, smagorinsky)
     else:
         raise ValueError(collision)
     if force is not None:
@@ -542,11 +565,11 @@ def step(f0, bc_mask, missing, bcs: Sequence[BC], omega, lat: Lattice, policy="F
     return f1
 
 
-def run(f0, bc_mask, missing, bcs, omega, lat, nsteps, policy="FP32FP32", collision="BGK", flavor="jax", force=None):
+def run(f0, bc_mask, missing, bcs, omega, lat, nsteps, policy="FP32FP32", collision="BGK", flavor="jax", force=None, smagorinsky=0.17):
     """The user loop of examples/performance/mlups_3d.py:77-80: step then swap."""
     f_a, f_b = f0, f0.copy()
     for _ in range(nsteps):
-        f_b = step(f_a, bc_mask, missing, bcs, omega, lat, policy, collision, flavor, f1_prev=f_b, force=force)
+        f_b = step(f_a, bc_mask, missing, bcs, omega, lat, policy, collision, flavor, f1_prev=f_b, force=force, smagorinsky=smagorinsky)
         f_a, f_b = f_b, f_a
     return f_a
 

@@ -12,7 +12,7 @@ enum {
 
 typedef struct LbmDesc {
   int d, q, nx, ny, nz;
-  int collision;   /* 0 BGK, 1 KBC */
+  int collision;   /* 0 BGK, 1 KBC, 2 SmagorinskyLESBGK */
   int compute;     /* 1 f32, 2 f64 */
   int store;       /* 0 f16, 1 f32, 2 f64 */
   double omega;
@@ -24,6 +24,9 @@ typedef struct LbmDesc {
   int bc_kind[256];
   double bc_rho[256];
   double bc_u[256 * 3];
+  int has_force;      /* ForcedCollision + ExactDifference (forced_collision.py:34-39) */
+  double force[3];
+  double smagorinsky; /* SmagorinskyLESBGK coefficient (smagorinsky_les_bgk.py:24) */
 } LbmDesc;
 
 #define REAL float

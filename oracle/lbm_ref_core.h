@@ -22,6 +22,8 @@ static inline void FN(store)(void* p, int store, long long i, REAL v) {
   }
 }
 
+static inline REAL FN(sqrt_)(REAL v) { return sizeof(REAL) == 4 ? (REAL)sqrtf((float)v) : (REAL)sqrt((double)v); }
+
 /* quadratic_equilibrium.py:35-60 */
 static void FN(equilibrium)(const LbmDesc* d, REAL rho, const REAL* u, REAL* feq) {
   REAL uu = 0;
@@ -211,8 +213,26 @@ static void FN(step)(const LbmDesc* d, void* f0, void* f1, const unsigned char* 
         FN(equilibrium)(d, rho, u, feq);
         if (d->collision == 0) {
           for (int l = 0; l < d->q; ++l) out[l] = f[l] - omega * (f[l] - feq[l]); /* bgk.py:30-34 */
-        } else {
+        } else if (d->collision == 1) {
           FN(collide_kbc)(d, f, feq, rho, omega, out);
+        } else { /* smagorinsky_les_bgk.py:37-90: 'strain' from squared fneq selected by the SIGNED sum of c_l */
+          REAL strain = 0;
+          for (int l = 0; l < d->q; ++l) {
+            const int cs_l = d->c[l] + d->c[27 + l] + d->c[54 + l];
+            const REAL fneq = f[l] - feq[l];
+            if (cs_l == 1) strain += fneq * fneq;
+            if (cs_l >= 2) strain += (REAL)2.0 * fneq * fneq;
+          }
+          const REAL tau0 = (REAL)1.0 / omega, coef = (REAL)d->smagorinsky;
+          const REAL tau = tau0 + (REAL)0.5 * (FN(sqrt_)(tau0 * tau0 + (REAL)36.0 * (coef * coef) * FN(sqrt_)(strain)) - tau0);
+          const REAL inv_tau = (REAL)1.0 / tau;
+          for (int l = 0; l < d->q; ++l) out[l] = f[l] - inv_tau * (f[l] - feq[l]);
+        }
+        if (d->has_force) { /* exact_difference_force.py:79-84: f += feq(rho, u + F) - feq(rho, u) */
+          REAL uf[3] = {0, 0, 0}, feq_force[27];
+          for (int a = 0; a < d->d; ++a) uf[a] = u[a] + (REAL)d->force[a];
+          FN(equilibrium)(d, rho, uf, feq_force);
+          for (int l = 0; l < d->q; ++l) out[l] += feq_force[l] - feq[l];
         }
         /* collision-step BCs and outflow aux: L374, L286-293 */
         if (kind == BC_FULLWAY) { /* bc_fullway_bounce_back.py:60-72 */

@@ -320,14 +320,201 @@ def _make_warp():
     return wp, utils
 
 
+# ---- interpretive `warp`: executes the reference's Warp kernels / functionals as the plain Python they are ---------------
+# Warp kernels are syntactically Python.  With small value-type vector classes (numpy-backed), `wp.func` = call with
+# by-value vector arguments, `wp.kernel` + `wp.launch` = a loop over the launch grid with `wp.tid()` returning the current
+# index, the reference's WARP backend (fused step kernel nse_stepper.py:344-381, every BC functional, the Warp masker, the
+# aux-data kernels) runs here cell by cell — slowly, but it IS the reference's code, and it pins the Warp-only semantics
+# (255 skip, scalar prescribed value kept in f_1[0], aux recovery, per-index interior flag of the masker) that the JAX
+# path cannot.  Typing follows Warp's: numpy scalars keep their width (NEP 50 makes Python literals weak, as in Warp),
+# Python floats handed to a launch become float32 (Warp's inference for `Any`-typed scalar arguments).
+class _VecBase(np.ndarray):
+    pass
+
+
+class WpArray(np.ndarray):
+    """numpy array with the two wp.array members the reference touches."""
+
+    def numpy(self):
+        return np.array(self, copy=True).view(np.ndarray)
+
+    @property
+    def ptr(self):
+        return self.ctypes.data
+
+
+_VEC_TYPES = {}
+
+
+def _vec_type(n, dtype):
+    key = (int(n), np.dtype(dtype))
+    if key not in _VEC_TYPES:
+        length, dt = key
+
+        class Vec(_VecBase):
+            def __new__(cls, *vals):
+                a = np.zeros(length, dtype=dt).view(cls)
+                if len(vals) == 1:
+                    a[:] = np.asarray(vals[0]).reshape(-1) if np.ndim(vals[0]) else vals[0]
+                elif vals:
+                    a[:] = vals
+                return a
+
+        Vec._length, Vec._scalar = length, dt
+        Vec.__name__ = f"vec{length}_{dt.name}"
+        _VEC_TYPES[key] = Vec
+    return _VEC_TYPES[key]
+
+
+def _mat_type(shape, dtype):
+    dt = np.dtype(dtype)
+
+    def make(values=None):
+        a = np.zeros(shape, dtype=dt)
+        if values is not None:
+            a[...] = np.asarray(values).reshape(shape)
+        return a
+
+    return make
+
+
+_TID = {"idx": None}
+
+
+class _ReadsFirst:
+    """One launch's view of an array: reads see the PRE-LAUNCH contents, writes go to the live array.
+
+    The reference's fused step kernel has a benign data race: while every thread pulls its neighbours' populations from
+    f_0, the aux-recovery step of Zou-He / Regularized cells writes f_1's old values back into f_0[opp[l], cell] for the
+    cell's missing directions (nse_stepper.py:318-342) — slots that the periodic-wrap neighbour on the opposite domain
+    face (a wall-edge cell) pulls in the same launch.  The raced values only ever reach cells behind a boundary (they
+    are bounced straight back out of the domain), but they are visible in the arrays.  A plain sequential loop would
+    resolve the race by launch-index order; this view resolves it as reads-before-writes, the one ordering whose result
+    does not depend on thread scheduling (no thread of a launch reads a slot it wrote itself, except through atomic_add,
+    which goes to the live array)."""
+
+    __slots__ = ("live", "snap", "shape", "dtype", "ndim")
+
+    def __init__(self, live):
+        self.live, self.snap = live, np.array(live, copy=True).view(np.ndarray)
+        self.shape, self.dtype, self.ndim = live.shape, live.dtype, live.ndim
+
+    def __getitem__(self, k):
+        return self.snap[k]
+
+    def __setitem__(self, k, v):
+        self.live[k] = v
+
+
+class _Kernel:
+    def __init__(self, fn):
+        self.fn = fn
+        self.__name__ = getattr(fn, "__name__", "kernel")
+
+
+def _make_warp_interp():
+    import functools
+
+    wp = _Permissive("warp")
+    wp.__interp__ = True
+    wp.constant = lambda x: x
+    wp.static = lambda x: x
+    wp.init = lambda *a, **k: None
+    wp.synchronize = lambda *a, **k: None
+    for n, t in (("float16", np.float16), ("float32", np.float32), ("float64", np.float64), ("uint8", np.uint8), ("int32", np.int32),
+                 ("int64", np.int64), ("bool", np.bool_)):  # fmt: skip
+        setattr(wp, n, t)
+
+    def vec(*args, length=None, dtype=None):
+        if args and length is not None:  # value form: wp.vec(x, length=n)   (bc_zouhe.py:113)
+            val = args[0]
+            return _vec_type(length, dtype or np.asarray(val).dtype)(val)
+        return _vec_type(args[0] if args else length, dtype)
+
+    wp.vec = vec
+    wp.mat = lambda shape, dtype=None: _mat_type(tuple(shape), dtype)
+    wp.vec2i, wp.vec3i = _vec_type(2, np.int32), _vec_type(3, np.int32)
+    wp.vec2, wp.vec3 = _vec_type(2, np.float32), _vec_type(3, np.float32)
+    wp.vec2f, wp.vec3f, wp.vec2d, wp.vec3d = wp.vec2, wp.vec3, _vec_type(2, np.float64), _vec_type(3, np.float64)
+
+    def func(fn):
+        @functools.wraps(fn)
+        def by_value(*a, **k):  # Warp vectors are value types: the callee works on its own copy
+            return fn(*(x.copy() if isinstance(x, _VecBase) else x for x in a), **k)
+
+        return by_value
+
+    wp.func = func
+    wp.kernel = lambda fn: _Kernel(fn)
+
+    def tid():
+        return _TID["idx"]
+
+    wp.tid = tid
+
+    def launch(kernel=None, dim=None, inputs=(), outputs=(), **kw):
+        dims = (int(dim),) if np.ndim(dim) == 0 else tuple(int(d) for d in dim)
+        args = [np.float32(a) if type(a) is float else (_ReadsFirst(a) if isinstance(a, WpArray) else a) for a in list(inputs) + list(outputs)]
+        for idx in np.ndindex(*dims):
+            _TID["idx"] = idx[0] if len(idx) == 1 else idx
+            kernel.fn(*args)
+        _TID["idx"] = None
+
+    wp.launch = launch
+
+    def _as_array(a, dtype=None):
+        return np.array(a, dtype=dtype, copy=True).view(WpArray)
+
+    wp.array = lambda data=None, dtype=None, **k: None if data is None else _as_array(data, dtype)
+    wp.from_numpy = lambda data, dtype=None, **k: _as_array(data, dtype)
+    def zeros(shape, dtype=np.float32, **k):
+        shape = (int(shape),) if np.ndim(shape) == 0 else tuple(shape)
+        if isinstance(dtype, type) and issubclass(dtype, _VecBase):  # array of vectors (momentum_transfer.py:166)
+            return np.zeros(shape + (dtype._length,), dtype=dtype._scalar).view(WpArray)
+        return np.zeros(shape, dtype=dtype).view(WpArray)
+
+    wp.zeros = zeros
+    wp.empty = zeros
+    wp.ones = lambda shape, dtype=np.float32, **k: np.ones(shape, dtype=dtype).view(WpArray)
+    wp.full = lambda shape, value, dtype=np.float32, **k: np.full(shape, value, dtype=dtype).view(WpArray)
+    wp.clone = lambda a, **k: np.array(a, copy=True).view(WpArray)
+    wp.to_jax = lambda a: np.asarray(a).view(np.ndarray)
+    wp.from_jax = lambda a, dtype=None: _as_array(a, dtype)
+
+    def copy(dest, src, **k):
+        dest[...] = src
+
+    wp.copy = copy
+    for n in ("array1d", "array2d", "array3d", "array4d"):
+        setattr(wp, n, lambda *a, **k: None)  # annotations only
+
+    def atomic_add(arr, *idx_and_value):
+        *idx, value = idx_and_value
+        arr = arr.live if isinstance(arr, _ReadsFirst) else arr
+        old = arr[tuple(idx)]
+        arr[tuple(idx)] = old + value
+        return old
+
+    wp.atomic_add = atomic_add
+    wp.abs, wp.sqrt, wp.min, wp.max = np.abs, np.sqrt, min, max
+    wp.dot = lambda a, b: (a * b).sum(dtype=a.dtype)
+    wp.length = lambda a: np.sqrt((a * a).sum(dtype=a.dtype))
+    wp.cw_div = lambda a, b: a / b
+    wp.cw_mul = lambda a, b: a * b
+    utils = _Permissive("warp.utils")
+    wp.utils = utils
+    return wp, utils
+
+
 _DUMMY_MODULES = (
     "trimesh", "pyvista", "matplotlib", "matplotlib.pylab", "matplotlib.pyplot", "matplotlib.cm", "cupy", "stl", "PIL",
     "PIL.Image", "pxr", "kvikio", "kvikio._lib", "kvikio._lib.arr", "mpi4py",
 )  # fmt: skip
 
 
-def install():
-    """Register the stand-ins in sys.modules (idempotent).  Refuses to shadow a real jax installation."""
+def install(interpret_warp=False):
+    """Register the stand-ins in sys.modules (idempotent).  Refuses to shadow a real jax installation.
+    interpret_warp: install the interpretive `warp` (runs the reference's WARP backend per cell) instead of the inert one."""
     if "jax" in sys.modules and not getattr(sys.modules["jax"], "__refshim__", False):
         raise RuntimeError("a real `jax` is already imported; the stand-in must not shadow it")
     if getattr(sys.modules.get("jax"), "__refshim__", False):
@@ -375,7 +562,7 @@ def install():
         "jax.experimental.mesh_utils": mesh_utils, "jax.experimental.shard_map": shard_map, "jax.image": image,
         "jax.dlpack": dlpack,
     }  # fmt: skip
-    wp, wp_utils = _make_warp()
+    wp, wp_utils = _make_warp_interp() if interpret_warp else _make_warp()
     mods["warp"], mods["warp.utils"] = wp, wp_utils
     for name in _DUMMY_MODULES:
         if name not in sys.modules:
@@ -388,9 +575,9 @@ def set_x64(enabled: bool):
     _X64["enabled"] = bool(enabled)
 
 
-def import_reference(path="/root/reference"):
+def import_reference(path="/root/reference", interpret_warp=False):
     """install() + import the reference package `xlb` from `path`; returns the module."""
-    install()
+    install(interpret_warp=interpret_warp)
     if path not in sys.path:
         sys.path.insert(0, path)
     import xlb  # noqa: the reference

@@ -27,6 +27,21 @@ STEP_CASES = [
 # gamma = <dh|ds>/(eps + <dh|dh>) becomes 0/0-like and the run is ill-conditioned — the numpy oracle in fp32 and in fp64
 # differ by 2e-3 after 60 steps — so it cannot pin anything.)
 EXTRA_CASES_2D = ["channel2d_d2q9_bgk_outflow_fp32", "channel2d_d2q9_bgk_zouhe_pressure_fp32"]
+# Produced by the reference's WARP backend itself, executed per cell under oracle/refshim's interpretive `warp`
+# (tests/golden/make_golden_warp.py).  All FP32FP32.
+WARP_CASES = [
+    "warp_cavity_d3q19_bgk",
+    "warp_cavity_d3q19_bgk_solid255",
+    "warp_cavity_d2q9_kbc",
+    "warp_tunnel_d3q27_kbc_regularized_outflow",
+    "warp_tunnel_d3q19_bgk_zouhe_pressure",
+    "warp_tunnel_d3q19_bgk_regularized_donothing",
+    "warp_channel2d_d2q9_bgk",
+    "warp_channel2d_d2q9_bgk_regpressure",
+    "warp_periodic_d3q27_kbc",
+]
+# ... and the collision / forcing options the CUDA path does not have yet: oracle-only for now
+WARP_CASES_N4 = ["warp_periodic_d3q19_bgk_forced", "warp_periodic_d3q19_smagorinsky", "warp_periodic_d3q27_smagorinsky_forced"]
 # relative tolerance (max |a-b| / max |b|) per store/compute policy; north-star: 1e-5 fp32, 1e-3 fp16 storage
 RTOL = {"FP32FP32": 1e-5, "FP64FP32": 1e-5, "FP64FP64": 1e-9, "FP32FP16": 1e-3, "FP64FP16": 1e-3}
 
@@ -38,6 +53,9 @@ def load_golden(name):
         g[k] = str(g[k])
     g["shape"] = tuple(int(s) for s in g["shape"])
     g["steps"], g["omega"], g["n_bc"] = int(g["steps"]), float(g["omega"]), int(g["n_bc"])
+    g["backend"] = str(g["backend"]) if "backend" in g else "JAX"
+    g["force_vector"] = g["force_vector"] if "force_vector" in g else None
+    g["smagorinsky"] = float(g["smagorinsky"]) if "smagorinsky" in g else 0.17
     g["bcs"] = []
     for i in range(g["n_bc"]):
         b = {k[len(f"bc{i}_") :]: g[k] for k in g if k.startswith(f"bc{i}_")}
@@ -74,7 +92,7 @@ def oracle_bcs(g):
     return out
 
 
-def oracle_run(g, steps=None, flavor="jax"):
+def oracle_masks(g, flavor="jax"):
     from oracle import lbm_numpy as O
 
     lat = O.Lattice(g["lattice"])
@@ -84,7 +102,29 @@ def oracle_run(g, steps=None, flavor="jax"):
     else:  # the stepper skips the masker when no BC carries indices (nse_stepper.py:115-116)
         bc_mask = np.zeros((1,) + g["shape"], np.uint8)
         missing = np.zeros((lat.q,) + g["shape"], bool)
-    f = O.run(g["f_init"].copy(), bc_mask, missing, bcs, g["omega"], lat, g["steps"] if steps is None else steps, policy=g["policy"], collision=g["collision"], flavor="jax")
+    if "solid255" in g:  # solid interior marked after the masker, as MeshBoundaryMasker does (mesh_boundary_masker.py:170-172)
+        bc_mask[0][tuple(g["solid255"])] = 255
+    return lat, bcs, bc_mask, missing
+
+
+def oracle_run(g, steps=None, flavor="jax"):
+    """numpy oracle on a fixture.  `flavor` picks the masker algorithm; the step itself follows the JAX path, plus the
+    Warp-only 255 skip for fixtures that came from the WARP backend."""
+    from oracle import lbm_numpy as O
+
+    lat, bcs, bc_mask, missing = oracle_masks(g, flavor)
+    f = O.run(g["f_init"].copy(), bc_mask, missing, bcs, g["omega"], lat, g["steps"] if steps is None else steps, policy=g["policy"], collision=g["collision"],
+              flavor="warp" if "solid255" in g else "jax", force=g["force_vector"], smagorinsky=g["smagorinsky"])  # fmt: skip
+    return f, bc_mask, missing
+
+
+def c_oracle_run(g, steps=None):
+    """C oracle (per-cell restatement of the Warp kernel) on a fixture, Warp masker."""
+    from oracle import lbm_c
+
+    lat, bcs, bc_mask, missing = oracle_masks(g, "warp")
+    f = lbm_c.run(g["f_init"].copy(), bc_mask, missing, bcs, g["omega"], lat, g["steps"] if steps is None else steps, g["policy"], g["collision"],
+                  force=g["force_vector"], smagorinsky=g["smagorinsky"])  # fmt: skip
     return f, bc_mask, missing
 
 
@@ -137,12 +177,15 @@ def native_case(g, backend="WARP", cells_per_thread=0):
             elif be == ComputeBackend.JAX:
                 bc = cls("velocity", profile=(lambda pv=pv: pv), indices=idx)
             else:  # Warp convention: per-cell callable returning the normal velocity magnitude (x-inlet: u_x)
-                bc = cls("velocity", profile=(lambda index, pv=pv: [pv[0][index[1], index[2]]]), indices=idx)
+                bc = cls("velocity", profile=(lambda index, pv=pv: [pv[0][index[1], index[2]] if pv[0].ndim == 2 else pv[0][index[1]]]), indices=idx)
         else:
             raise ValueError(kind)
         bc.id = b["id"]
         bcs.append(bc)
-    stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=bcs, collision_type=g["collision"], cells_per_thread=cells_per_thread)
+    kw = {} if g.get("force_vector") is None else dict(force_vector=np.asarray(g["force_vector"], dtype=np.float64))
+    stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=bcs, collision_type=g["collision"], cells_per_thread=cells_per_thread, **kw)
+    if g["collision"] == "SmagorinskyLESBGK":
+        (stepper.collision.collision_operator if kw else stepper.collision).smagorinsky_coef = g.get("smagorinsky", 0.17)
     # the reference's JAX path keeps the initial state in the compute dtype; here populations always live in the store dtype
     f_init = g["f_init"].astype(pp.store_precision.np_dtype)
     if be == ComputeBackend.WARP and len(g["shape"]) == 2:
@@ -152,6 +195,9 @@ def native_case(g, backend="WARP", cells_per_thread=0):
         return xlb.field.as_field(torch.as_tensor(np.ascontiguousarray(f_init)), device=grid.device)
 
     f_0, f_1, bc_mask, missing_mask = stepper.prepare_fields(initializer=initializer)
+    if "solid255" in g:  # solid interior marked after the masker, as MeshBoundaryMasker does
+        idx = torch.as_tensor(np.asarray(g["solid255"]), device=bc_mask.device)
+        bc_mask[(0,) + tuple(idx[a] for a in range(idx.shape[0]))] = 255
     return stepper, f_0, f_1, bc_mask, missing_mask
 
 

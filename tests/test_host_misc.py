@@ -83,6 +83,37 @@ def test_stepper_rejects_out_of_scope_options_loudly():
     pp = xlb.PrecisionPolicy.FP32FP32
     xlb.init(velocity_set=xlb.velocity_set.D3Q19(pp, ComputeBackend.WARP), default_backend=ComputeBackend.WARP, default_precision_policy=pp)
     g = grid_factory((4, 4, 4), device="cpu")
-    for kw in (dict(collision_type="SmagorinskyLESBGK"), dict(force_vector=np.zeros(3)), dict(streaming_scheme="push"), dict(collision_type="KBC")):
+    for kw in (dict(collision_type="MRT"), dict(streaming_scheme="push"), dict(collision_type="KBC")):
         with pytest.raises(NotImplementedError):
             IncompressibleNavierStokesStepper(grid=g, boundary_conditions=[], **kw)
+    with pytest.raises(AssertionError):  # forced_collision.py:30 "Check the dimensions of the input force!"
+        IncompressibleNavierStokesStepper(grid=g, boundary_conditions=[], force_vector=np.zeros(2))
+    with pytest.raises(AssertionError):  # forced_collision.py:27: only "exact_difference" exists
+        IncompressibleNavierStokesStepper(grid=g, boundary_conditions=[], force_vector=np.zeros(3), forcing_scheme="guo")
+
+
+def test_stepper_collision_options_mirror_the_reference_ctor():
+    """nse_stepper.py:38-46: collision_type in {BGK, KBC, SmagorinskyLESBGK}, optionally wrapped by ForcedCollision."""
+    import xlb_b200 as xlb
+    from xlb_b200 import native
+    from xlb_b200.compute_backend import ComputeBackend
+    from xlb_b200.grid import grid_factory
+    from xlb_b200.operator.collision import BGK, KBC, ForcedCollision, SmagorinskyLESBGK
+    from xlb_b200.operator.force import ExactDifference
+    from xlb_b200.operator.stepper import IncompressibleNavierStokesStepper
+
+    pp = xlb.PrecisionPolicy.FP32FP32
+    xlb.init(velocity_set=xlb.velocity_set.D3Q27(pp, ComputeBackend.WARP), default_backend=ComputeBackend.WARP, default_precision_policy=pp)
+    g = grid_factory((4, 4, 4), device="cpu")
+    s = IncompressibleNavierStokesStepper(grid=g, collision_type="SmagorinskyLESBGK")
+    assert isinstance(s.collision, SmagorinskyLESBGK) and s.collision.smagorinsky_coef == 0.17 and s.collision.native_collision == native.SMAGORINSKY_LES_BGK
+    s = IncompressibleNavierStokesStepper(grid=g, collision_type="KBC", force_vector=np.array([1e-5, 0.0, 0.0]))
+    assert isinstance(s.collision, ForcedCollision) and isinstance(s.collision.collision_operator, KBC)
+    assert isinstance(s.collision.forcing_operator, ExactDifference)
+    assert s.collision.native_collision == native.KBC | native.COLLISION_FORCED and list(s.collision.native_force) == [1e-5, 0.0, 0.0]
+    s = IncompressibleNavierStokesStepper(grid=g, collision_type="SmagorinskyLESBGK", force_vector=np.array([0.0, 2e-5, 0.0]))
+    assert s.collision.native_collision == native.SMAGORINSKY_LES_BGK | native.COLLISION_FORCED and s.collision.native_smagorinsky == 0.17
+    assert isinstance(IncompressibleNavierStokesStepper(grid=g).collision, BGK)
+    xlb.init(velocity_set=xlb.velocity_set.D2Q9(pp, ComputeBackend.WARP), default_backend=ComputeBackend.WARP, default_precision_policy=pp)
+    with pytest.raises(NotImplementedError):  # the reference functional reads c[2, l]: 3-D only
+        SmagorinskyLESBGK()

@@ -1,7 +1,8 @@
 """The two CPU oracles are independent restatements of the reference (whole-array numpy after the JAX path, per-cell C
 after the Warp kernel).  Seeded random set-ups — random extents, relaxation rates, obstacles and boundary sets — must give
 the same populations from both; and, where /root/reference is mounted (build container only), the reference's own
-Python run live under the numpy `jax` stand-in must agree with them too."""
+Python run live — its JAX backend under the numpy `jax` stand-in, its WARP backend under the interpretive `warp` stand-in —
+must agree with them too."""
 
 import os
 import subprocess
@@ -101,3 +102,54 @@ def test_reference_run_live_matches_the_oracle():
     out = dict(line.split(" ", 1) for line in proc.stdout.splitlines() if line.startswith(("MASKS", "RELERR")))
     assert out["MASKS"].strip() == "True"
     assert float(out["RELERR"]) <= 1e-7
+
+
+LIVE_WARP = r"""
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+from oracle import refshim
+xlb = refshim.import_reference("/root/reference", interpret_warp=True)
+from xlb.compute_backend import ComputeBackend
+from xlb.precision_policy import PrecisionPolicy
+from xlb.grid import grid_factory
+from xlb.operator.stepper import IncompressibleNavierStokesStepper
+from xlb.operator.boundary_condition import FullwayBounceBackBC, ZouHeBC, ExtrapolationOutflowBC, HalfwayBounceBackBC
+from oracle import lbm_numpy as O
+from oracle import lbm_c
+pp, be = PrecisionPolicy.FP32FP32, ComputeBackend.WARP
+xlb.init(velocity_set=xlb.velocity_set.D3Q19(precision_policy=pp, compute_backend=be), default_backend=be, default_precision_policy=pp)
+shape = (12, 7, 7)
+grid = grid_factory(shape)
+box, bne = grid.bounding_box_indices(), grid.bounding_box_indices(remove_edges=True)
+walls = [box["bottom"][i] + box["top"][i] + box["front"][i] + box["back"][i] for i in range(3)]
+walls = np.unique(np.array(walls), axis=-1).tolist()
+block = [[4, 4, 5, 5], [3, 3, 3, 3], [3, 4, 3, 4]]
+bcs = [FullwayBounceBackBC(indices=walls), ZouHeBC("velocity", prescribed_value=(0.03, 0.0, 0.0), indices=bne["left"]),
+       ExtrapolationOutflowBC(indices=bne["right"]), HalfwayBounceBackBC(indices=block)]
+stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=bcs, collision_type="BGK")
+f_0, f_1, bc_mask, missing = stepper.prepare_fields()
+for i in range(6):
+    f_0, f_1 = stepper(f_0, f_1, bc_mask, missing, 1.5, i)
+    f_0, f_1 = f_1, f_0
+lat = O.Lattice("D3Q19")
+obcs = [O.BC("fullway", bcs[0].id, np.array(walls)), O.BC("zouhe", bcs[1].id, np.array(bne["left"]), bc_type="velocity", prescribed=np.array([0.03, 0.0, 0.0])),
+        O.BC("outflow", bcs[2].id, np.array(bne["right"])), O.BC("halfway", bcs[3].id, np.array(block))]
+bm, mm = O.build_masks(obcs, shape, lat, flavor="warp")
+f = lbm_c.run(O.initialize_eq(shape, lat), bm, mm, obcs, 1.5, lat, 6, "FP32FP32", "BGK")
+ref = np.asarray(f_0)
+print("MASKS", np.array_equal(bm, np.asarray(bc_mask)) and np.array_equal(mm, np.asarray(missing)))
+print("EXACT", np.array_equal(f, ref), float(np.abs(f - ref).max()))
+"""
+
+
+@needs_c
+@pytest.mark.skipif(not os.path.isdir("/root/reference/xlb"), reason="the reference is only mounted in the build container")
+def test_reference_warp_backend_live_equals_the_c_oracle():
+    """Executes the reference's WARP backend right now (its fused kernel, BC functionals and Warp masker interpreted per
+    cell by oracle/refshim's `warp` stand-in) and requires the C oracle — the restatement of that kernel — to match it
+    bit for bit."""
+    proc = subprocess.run([sys.executable, "-c", LIVE_WARP % {"root": ROOT}], capture_output=True, text=True, timeout=600, cwd="/tmp")
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    out = dict(line.split(" ", 1) for line in proc.stdout.splitlines() if line.startswith(("MASKS", "EXACT")))
+    assert out["MASKS"].strip() == "True"
+    assert out["EXACT"].split()[0] == "True", out["EXACT"]

@@ -12,6 +12,9 @@ struct xlbn_stepper {
   double eq_omega;       // omega the EquilibriumBC constants in the table were computed for (NaN = never)
   xlbn::BcEntry* table;  // device, 256 entries
   int device;
+  bool forced;           // ForcedCollision (xlbn_stepper_set_force)
+  double force[3];
+  double smagorinsky;
 };
 
 using namespace xlbn;
@@ -22,6 +25,17 @@ template <> int dispatch_step<D3Q27, XLBN_BGK>(const StepCall&);
 template <> int dispatch_step<D3Q27, XLBN_KBC>(const StepCall&);
 template <> int dispatch_step<D2Q9, XLBN_BGK>(const StepCall&);
 template <> int dispatch_step<D2Q9, XLBN_KBC>(const StepCall&);
+// extended collision models (step_inst_ext_*.cu)
+constexpr int kF = XLBN_COLLISION_FORCED;
+template <> int dispatch_step<D3Q19, XLBN_BGK | kF>(const StepCall&);
+template <> int dispatch_step<D3Q19, XLBN_SMAGORINSKY_LES_BGK>(const StepCall&);
+template <> int dispatch_step<D3Q19, XLBN_SMAGORINSKY_LES_BGK | kF>(const StepCall&);
+template <> int dispatch_step<D3Q27, XLBN_BGK | kF>(const StepCall&);
+template <> int dispatch_step<D3Q27, XLBN_KBC | kF>(const StepCall&);
+template <> int dispatch_step<D3Q27, XLBN_SMAGORINSKY_LES_BGK>(const StepCall&);
+template <> int dispatch_step<D3Q27, XLBN_SMAGORINSKY_LES_BGK | kF>(const StepCall&);
+template <> int dispatch_step<D2Q9, XLBN_BGK | kF>(const StepCall&);
+template <> int dispatch_step<D2Q9, XLBN_KBC | kF>(const StepCall&);
 }  // namespace xlbn
 
 extern "C" {
@@ -52,7 +66,10 @@ int xlbn_lattice_tables(int lattice, int32_t* c, double* w, int32_t* opp) {
 int xlbn_stepper_create(const xlbn_stepper_desc* desc, xlbn_stepper** out) {
   if (!desc || !out) return fail(XLBN_E_ARG, "stepper_create: NULL argument");
   if (desc->lattice < XLBN_D2Q9 || desc->lattice > XLBN_D3Q27) return fail(XLBN_E_ARG, "stepper_create: unknown lattice %d", desc->lattice);
-  if (desc->collision != XLBN_BGK && desc->collision != XLBN_KBC) return fail(XLBN_E_ARG, "stepper_create: unknown collision %d", desc->collision);
+  if (desc->collision != XLBN_BGK && desc->collision != XLBN_KBC && desc->collision != XLBN_SMAGORINSKY_LES_BGK)
+    return fail(XLBN_E_ARG, "stepper_create: unknown collision %d", desc->collision);
+  if (desc->collision == XLBN_SMAGORINSKY_LES_BGK && desc->lattice == XLBN_D2Q9)
+    return fail(XLBN_E_UNSUPPORTED, "SmagorinskyLESBGK: 3-D velocity sets only (the reference functional reads c[2, l]: smagorinsky_les_bgk.py:71-76)");
   if (desc->collision == XLBN_KBC && desc->lattice == XLBN_D3Q19)
     return fail(XLBN_E_UNSUPPORTED, "KBC: velocity set not supported: D3Q19 (reference: kbc.py:71-72, 184-185)");
   if (desc->compute_dtype != XLBN_F32 && desc->compute_dtype != XLBN_F64) return fail(XLBN_E_DTYPE, "stepper_create: compute dtype %d", desc->compute_dtype);
@@ -89,6 +106,9 @@ int xlbn_stepper_create(const xlbn_stepper_desc* desc, xlbn_stepper** out) {
     s->has_equilibrium_bc |= host[i].kind == XLBN_BC_EQUILIBRIUM;
   }
   s->eq_omega = nan("");
+  s->forced = false;
+  s->force[0] = s->force[1] = s->force[2] = 0.0;
+  s->smagorinsky = 0.17;  // smagorinsky_les_bgk.py:24
   cudaError_t e = cudaGetDevice(&s->device);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->table), sizeof(host));
   if (e == cudaSuccess) e = cudaMemcpy(s->table, host, sizeof(host), cudaMemcpyHostToDevice);
@@ -105,6 +125,21 @@ int xlbn_stepper_destroy(xlbn_stepper* s) {
   if (!s) return 0;
   if (s->table) cudaFree(s->table);
   delete s;
+  return 0;
+}
+
+int xlbn_stepper_set_force(xlbn_stepper* s, const double* force) {
+  if (!s) return fail(XLBN_E_ARG, "stepper_set_force: NULL stepper");
+  s->forced = force != nullptr;
+  for (int a = 0; a < 3; ++a) s->force[a] = (force && a < (s->lattice == XLBN_D2Q9 ? 2 : 3)) ? force[a] : 0.0;
+  return 0;
+}
+
+int xlbn_stepper_set_smagorinsky(xlbn_stepper* s, double coefficient) {
+  if (!s) return fail(XLBN_E_ARG, "stepper_set_smagorinsky: NULL stepper");
+  if (s->collision != XLBN_SMAGORINSKY_LES_BGK) return fail(XLBN_E_STATE, "stepper_set_smagorinsky: the stepper's collision is not SmagorinskyLESBGK");
+  if (!(coefficient >= 0.0)) return fail(XLBN_E_ARG, "stepper_set_smagorinsky: coefficient %g", coefficient);
+  s->smagorinsky = coefficient;
   return 0;
 }
 
@@ -136,6 +171,8 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
   c.stream = (cudaStream_t)stream;
   c.ghost_lo = c.ghost_hi = nullptr;
   c.out_lo = c.out_hi = nullptr;
+  for (int a = 0; a < 3; ++a) c.force[a] = s->force[a];  // physical components; the cell algebra uses L::c(), not kernel axes
+  c.smagorinsky = s->smagorinsky;
   if (s->lattice == XLBN_D2Q9) {  // run [q][nx][ny] as kernel extents (1, nx, ny): unit-stride axis = thread axis
     if (halo) return fail(XLBN_E_UNSUPPORTED, "xlbn_step: x-slab halo is not available for 2-D lattices");
     if (dom->x_begin != 0 || dom->x_count != dom->nx) return fail(XLBN_E_UNSUPPORTED, "xlbn_step: partial x range is not available for 2-D lattices");
@@ -161,12 +198,36 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
     c.out_hi = halo_ghost(halo, halo->peer_hi, p_out, 0);
     c.out_lo = halo_ghost(halo, halo->peer_lo, p_out, 1);
   }
+  const int coll = s->collision | (s->forced ? kF : 0);
   switch (s->lattice) {
-    case XLBN_D3Q19: return dispatch_step<D3Q19, XLBN_BGK>(c);
-    case XLBN_D3Q27: return s->collision == XLBN_BGK ? dispatch_step<D3Q27, XLBN_BGK>(c) : dispatch_step<D3Q27, XLBN_KBC>(c);
-    case XLBN_D2Q9: return s->collision == XLBN_BGK ? dispatch_step<D2Q9, XLBN_BGK>(c) : dispatch_step<D2Q9, XLBN_KBC>(c);
+    case XLBN_D3Q19:
+      switch (coll) {
+        case XLBN_BGK: return dispatch_step<D3Q19, XLBN_BGK>(c);
+        case XLBN_BGK | kF: return dispatch_step<D3Q19, XLBN_BGK | kF>(c);
+        case XLBN_SMAGORINSKY_LES_BGK: return dispatch_step<D3Q19, XLBN_SMAGORINSKY_LES_BGK>(c);
+        case XLBN_SMAGORINSKY_LES_BGK | kF: return dispatch_step<D3Q19, XLBN_SMAGORINSKY_LES_BGK | kF>(c);
+      }
+      break;
+    case XLBN_D3Q27:
+      switch (coll) {
+        case XLBN_BGK: return dispatch_step<D3Q27, XLBN_BGK>(c);
+        case XLBN_KBC: return dispatch_step<D3Q27, XLBN_KBC>(c);
+        case XLBN_BGK | kF: return dispatch_step<D3Q27, XLBN_BGK | kF>(c);
+        case XLBN_KBC | kF: return dispatch_step<D3Q27, XLBN_KBC | kF>(c);
+        case XLBN_SMAGORINSKY_LES_BGK: return dispatch_step<D3Q27, XLBN_SMAGORINSKY_LES_BGK>(c);
+        case XLBN_SMAGORINSKY_LES_BGK | kF: return dispatch_step<D3Q27, XLBN_SMAGORINSKY_LES_BGK | kF>(c);
+      }
+      break;
+    case XLBN_D2Q9:
+      switch (coll) {
+        case XLBN_BGK: return dispatch_step<D2Q9, XLBN_BGK>(c);
+        case XLBN_KBC: return dispatch_step<D2Q9, XLBN_KBC>(c);
+        case XLBN_BGK | kF: return dispatch_step<D2Q9, XLBN_BGK | kF>(c);
+        case XLBN_KBC | kF: return dispatch_step<D2Q9, XLBN_KBC | kF>(c);
+      }
+      break;
   }
-  return fail(XLBN_E_ARG, "xlbn_step: bad stepper");
+  return fail(XLBN_E_ARG, "xlbn_step: bad stepper (lattice %d, collision %d)", s->lattice, coll);
 }
 
 }  // extern "C"

@@ -161,6 +161,64 @@ XLBN_DEV void collide_cell(TC (&f)[L::Q], TC omega) {
   XLBN_FOR(L::Q, l) f[l] = out[l]; XLBN_END
 }
 
+// ---- extended collision models ------------------------------------------------------------------
+// COLL = base operator (low two bits) | XLBN_COLLISION_FORCED.
+template <int COLL>
+constexpr int kBaseCollision = COLL & 3;
+template <int COLL>
+constexpr bool kForcedCollision = (COLL & XLBN_COLLISION_FORCED) != 0;
+
+__device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+
+// SmagorinskyLESBGK (reference: smagorinsky_les_bgk.py:37-90; a Warp functional only, which reads c[2, l]: 3-D lattices).
+// Restated literally: the 'strain' is a sum of squared non-equilibrium populations selected by the SIGNED component
+// sum of c_l (== 1: weight 1, >= 2: weight 2), in l order; tau = tau0 + (sqrt(tau0^2 + 36 C^2 sqrt(strain)) - tau0)/2.
+template <class L, class TC>
+XLBN_DEV void collide_smagorinsky(const TC (&f)[L::Q], const TC (&feq)[L::Q], TC omega, TC coef, TC (&out)[L::Q]) {
+  static_assert(L::D == 3, "SmagorinskyLESBGK: 3-D lattices only (the reference functional indexes c[2, l])");
+  TC strain = TC(0);
+  XLBN_FOR(L::Q, l)
+    constexpr int csum = L::c(0, l) + L::c(1, l) + L::c(2, l);
+    if constexpr (csum >= 1) {
+      const TC fneq = f[l] - feq[l];
+      if constexpr (csum == 1) strain = fma_(fneq, fneq, strain);
+      else strain = fma_(TC(2.0) * fneq, fneq, strain);
+    }
+  XLBN_END
+  const TC tau0 = TC(1.0) / omega;
+  const TC tau = tau0 + TC(0.5) * (sqrt_(fma_(tau0, tau0, TC(36.0) * (coef * coef) * sqrt_(strain))) - tau0);
+  const TC inv_tau = TC(1.0) / tau;
+  XLBN_FOR(L::Q, l) out[l] = fma_(-inv_tau, f[l] - feq[l], f[l]); XLBN_END
+}
+
+// ExactDifference forcing (reference: exact_difference_force.py:79-84): out += feq(rho, u + F) - feq(rho, u)
+template <class L, class TC>
+XLBN_DEV void exact_difference(TC rho, const TC (&u)[L::D], const TC (&feq)[L::Q], const TC (&force)[L::D], TC (&out)[L::Q]) {
+  TC uf[L::D], feq_force[L::Q];
+  XLBN_FOR(L::D, d) uf[d] = u[d] + force[d]; XLBN_END
+  equilibrium<L, TC>(rho, uf, feq_force);
+  XLBN_FOR(L::Q, l) out[l] += feq_force[l] - feq[l]; XLBN_END
+}
+
+// macroscopic -> equilibrium -> collision [-> forcing] on one cell, in place, for every operator incl. the extended ones
+// (reference: nse_stepper.py:369-371 with self.collision = ForcedCollision(...), L45-46).
+template <class L, int COLL, class TC, bool FAST = false>
+XLBN_DEV void collide_cell_ext(TC (&f)[L::Q], TC omega, const double* force, double smagorinsky) {
+  TC rho, u[L::D], feq[L::Q], out[L::Q];
+  macroscopic<L, TC, FAST>(f, rho, u);
+  equilibrium<L, TC>(rho, u, feq);
+  if constexpr (kBaseCollision<COLL> == XLBN_BGK) collide_bgk<L, TC>(f, feq, omega, out);
+  else if constexpr (kBaseCollision<COLL> == XLBN_KBC) collide_kbc<L, TC, FAST>(f, feq, rho, omega, out);
+  else collide_smagorinsky<L, TC>(f, feq, omega, (TC)smagorinsky, out);
+  if constexpr (kForcedCollision<COLL>) {
+    TC fv[L::D];
+    XLBN_FOR(L::D, d) fv[d] = (TC)force[d]; XLBN_END
+    exact_difference<L, TC>(rho, u, feq, fv, out);
+  }
+  XLBN_FOR(L::Q, l) f[l] = out[l]; XLBN_END
+}
+
 // ---- boundary-condition functionals -------------------------------------------------------------------------------
 // `miss` bit l <=> missing_mask[l, cell].
 

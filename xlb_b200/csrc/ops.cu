@@ -132,6 +132,54 @@ __global__ void collide_kernel(const void* f, int f_dt, const void* feq, int feq
   XLBN_FOR(L::Q, l) store_as<TC>(fout, fout_dt, (long long)l * d.n + i, out[l]); XLBN_END
 }
 
+// Any operator incl. SmagorinskyLESBGK and the ForcedCollision wrapper (smagorinsky_les_bgk.py:92-138, forced_collision.py:41-103):
+// like the reference functionals it works on the GIVEN feq / rho / u, nothing is recomputed from f.
+struct Force3 {
+  double v[3];
+};
+template <class L, int COLL, class TC>
+__global__ void collide_ext_kernel(const void* f, int f_dt, const void* feq, int feq_dt, void* fout, int fout_dt, const void* rho, int rho_dt,
+                                   const void* u, int u_dt, TC omega, Force3 force, TC smagorinsky, Dims d) {
+  XLBN_CELL_INDEX();
+  TC ff[L::Q], fe[L::Q], out[L::Q];
+  XLBN_FOR(L::Q, l)
+    ff[l] = load_as<TC>(f, f_dt, (long long)l * d.n + i);
+    fe[l] = load_as<TC>(feq, feq_dt, (long long)l * d.n + i);
+  XLBN_END
+  TC r = TC(1);
+  if constexpr (kBaseCollision<COLL> == XLBN_KBC || kForcedCollision<COLL>) r = load_as<TC>(rho, rho_dt, i);
+  if constexpr (kBaseCollision<COLL> == XLBN_BGK) collide_bgk<L, TC>(ff, fe, omega, out);
+  else if constexpr (kBaseCollision<COLL> == XLBN_KBC) collide_kbc<L, TC>(ff, fe, r, omega, out);
+  else if constexpr (L::D == 3) collide_smagorinsky<L, TC>(ff, fe, omega, smagorinsky, out);
+  if constexpr (kForcedCollision<COLL>) {
+    TC uu[L::D], fv[L::D];
+    XLBN_FOR(L::D, a)
+      uu[a] = load_as<TC>(u, u_dt, (long long)a * d.n + i);
+      fv[a] = (TC)force.v[a];
+    XLBN_END
+    exact_difference<L, TC>(r, uu, fe, fv, out);
+  }
+  XLBN_FOR(L::Q, l) store_as<TC>(fout, fout_dt, (long long)l * d.n + i, out[l]); XLBN_END
+}
+
+// ExactDifference stand-alone (exact_difference_force.py:87-125)
+template <class L, class TC>
+__global__ void exact_difference_kernel(const void* fpc, int fpc_dt, const void* feq, int feq_dt, void* fout, int fout_dt, const void* rho, int rho_dt,
+                                        const void* u, int u_dt, Force3 force, Dims d) {
+  XLBN_CELL_INDEX();
+  TC out[L::Q], fe[L::Q], uu[L::D], fv[L::D];
+  XLBN_FOR(L::Q, l)
+    out[l] = load_as<TC>(fpc, fpc_dt, (long long)l * d.n + i);
+    fe[l] = load_as<TC>(feq, feq_dt, (long long)l * d.n + i);
+  XLBN_END
+  XLBN_FOR(L::D, a)
+    uu[a] = load_as<TC>(u, u_dt, (long long)a * d.n + i);
+    fv[a] = (TC)force.v[a];
+  XLBN_END
+  exact_difference<L, TC>(load_as<TC>(rho, rho_dt, i), uu, fe, fv, out);
+  XLBN_FOR(L::Q, l) store_as<TC>(fout, fout_dt, (long long)l * d.n + i, out[l]); XLBN_END
+}
+
 // ---- Generic stand-alone boundary-condition kernel (boundary_condition.py:83-117) -------------------------------------
 // f_0 := f_pre array, f_1 := f_post array, exactly as the reference passes them to the functional.
 // bc_functional applies one BC's functional to one cell: f holds f_post on entry and the BC's result on exit.
@@ -340,6 +388,77 @@ int xlbn_collide(int lattice, int collision, int compute_dtype, const void* f, i
     return fail(XLBN_E_ARG, "unknown collision %d", collision);
   }
   XLBN_LAUNCH_OK("collide_kernel");
+  return 0;
+}
+
+int xlbn_collide_ext(int lattice, int collision, int compute_dtype, const void* f, int f_dtype, const void* feq, int feq_dtype, void* fout,
+                     int fout_dtype, const void* rho, int rho_dtype, const void* u, int u_dtype, double omega, const double* force,
+                     double smagorinsky, const int32_t dims[3], void* stream) {
+  if (int e = check_dims(lattice, dims)) return e;
+  if (!f || !feq || !fout) return fail(XLBN_E_ARG, "xlbn_collide_ext: NULL array");
+  XLBN_REQUIRE_FLOAT(f_dtype, "f");
+  XLBN_REQUIRE_FLOAT(feq_dtype, "feq");
+  XLBN_REQUIRE_FLOAT(fout_dtype, "fout");
+  const int base = collision & 3;
+  const bool forced = (collision & XLBN_COLLISION_FORCED) != 0;
+  if (collision < 0 || (collision & ~(3 | XLBN_COLLISION_FORCED)) || base == 3) return fail(XLBN_E_ARG, "unknown collision %d", collision);
+  if (base == XLBN_KBC && lattice == XLBN_D3Q19) return fail(XLBN_E_UNSUPPORTED, "KBC: velocity set not supported: D3Q19 (reference: kbc.py:71-72, 184-185)");
+  if (base == XLBN_SMAGORINSKY_LES_BGK && lattice == XLBN_D2Q9)
+    return fail(XLBN_E_UNSUPPORTED, "SmagorinskyLESBGK: 3-D velocity sets only (reference: smagorinsky_les_bgk.py:71-76)");
+  if (base == XLBN_KBC || forced) {
+    if (!rho) return fail(XLBN_E_ARG, "xlbn_collide_ext: this operator needs rho");
+    XLBN_REQUIRE_FLOAT(rho_dtype, "rho");
+  }
+  Force3 fv = {{0.0, 0.0, 0.0}};
+  if (forced) {
+    if (!u || !force) return fail(XLBN_E_ARG, "xlbn_collide_ext: a forced operator needs u and the force vector");
+    XLBN_REQUIRE_FLOAT(u_dtype, "u");
+    for (int a = 0; a < (lattice == XLBN_D2Q9 ? 2 : 3); ++a) fv.v[a] = force[a];
+  }
+  const Dims d = kernel_dims(lattice, dims);
+  cudaStream_t st = (cudaStream_t)stream;
+#define XLBN_LAUNCH_COLLIDE_EXT(LAT, COLL)                                                                                                    \
+  {                                                                                                                                           \
+    using L = LAT;                                                                                                                            \
+    XLBN_COMPUTE_SWITCH(compute_dtype, collide_ext_kernel<L, COLL, TC><<<grid_for(d.n), 256, 0, st>>>(                                         \
+                                           f, f_dtype, feq, feq_dtype, fout, fout_dtype, rho, rho_dtype, u, u_dtype, (TC)omega, fv, (TC)smagorinsky, d)); \
+  }
+#define XLBN_COLLIDE_EXT_CASE(LAT, COLL)                                      \
+  if (!forced) XLBN_LAUNCH_COLLIDE_EXT(LAT, COLL)                             \
+  else XLBN_LAUNCH_COLLIDE_EXT(LAT, COLL | XLBN_COLLISION_FORCED)
+  if (lattice == XLBN_D3Q19) {
+    if (base == XLBN_BGK) { XLBN_COLLIDE_EXT_CASE(D3Q19, XLBN_BGK) }
+    else { XLBN_COLLIDE_EXT_CASE(D3Q19, XLBN_SMAGORINSKY_LES_BGK) }
+  } else if (lattice == XLBN_D3Q27) {
+    if (base == XLBN_BGK) { XLBN_COLLIDE_EXT_CASE(D3Q27, XLBN_BGK) }
+    else if (base == XLBN_KBC) { XLBN_COLLIDE_EXT_CASE(D3Q27, XLBN_KBC) }
+    else { XLBN_COLLIDE_EXT_CASE(D3Q27, XLBN_SMAGORINSKY_LES_BGK) }
+  } else {
+    if (base == XLBN_BGK) { XLBN_COLLIDE_EXT_CASE(D2Q9, XLBN_BGK) }
+    else { XLBN_COLLIDE_EXT_CASE(D2Q9, XLBN_KBC) }
+  }
+#undef XLBN_COLLIDE_EXT_CASE
+#undef XLBN_LAUNCH_COLLIDE_EXT
+  XLBN_LAUNCH_OK("collide_ext_kernel");
+  return 0;
+}
+
+int xlbn_exact_difference(int lattice, int compute_dtype, const void* f_postcollision, int f_dtype, const void* feq, int feq_dtype, void* fout,
+                          int fout_dtype, const void* rho, int rho_dtype, const void* u, int u_dtype, const double* force, const int32_t dims[3],
+                          void* stream) {
+  if (int e = check_dims(lattice, dims)) return e;
+  if (!f_postcollision || !feq || !fout || !rho || !u || !force) return fail(XLBN_E_ARG, "xlbn_exact_difference: NULL argument");
+  XLBN_REQUIRE_FLOAT(f_dtype, "f_postcollision");
+  XLBN_REQUIRE_FLOAT(feq_dtype, "feq");
+  XLBN_REQUIRE_FLOAT(fout_dtype, "fout");
+  XLBN_REQUIRE_FLOAT(rho_dtype, "rho");
+  XLBN_REQUIRE_FLOAT(u_dtype, "u");
+  Force3 fv = {{0.0, 0.0, 0.0}};
+  for (int a = 0; a < (lattice == XLBN_D2Q9 ? 2 : 3); ++a) fv.v[a] = force[a];
+  const Dims d = kernel_dims(lattice, dims);
+  XLBN_LATTICE_SWITCH(lattice, XLBN_COMPUTE_SWITCH(compute_dtype, exact_difference_kernel<L, TC><<<grid_for(d.n), 256, 0, (cudaStream_t)stream>>>(
+                                                                      f_postcollision, f_dtype, feq, feq_dtype, fout, fout_dtype, rho, rho_dtype, u, u_dtype, fv, d)));
+  XLBN_LAUNCH_OK("exact_difference_kernel");
   return 0;
 }
 

@@ -1,0 +1,9 @@
+// Explicit instantiation of the fused step kernel for D3Q19 with the extended collision models:
+// SmagorinskyLESBGK and the ForcedCollision / ExactDifference wrapper.  One cell per thread, all precision policies.
+#include "step_kernel.cuh"
+
+namespace xlbn {
+XLBN_DEFINE_STEP_DISPATCH(D3Q19, XLBN_BGK | XLBN_COLLISION_FORCED)
+XLBN_DEFINE_STEP_DISPATCH(D3Q19, XLBN_SMAGORINSKY_LES_BGK)
+XLBN_DEFINE_STEP_DISPATCH(D3Q19, XLBN_SMAGORINSKY_LES_BGK | XLBN_COLLISION_FORCED)
+}  // namespace xlbn

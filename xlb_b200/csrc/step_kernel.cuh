@@ -69,6 +69,9 @@ struct StepParams {
   long long plane;  // ny * nz
   long long n;      // nx * ny * nz  (population stride)
   double omega;
+  // extended collision models only (appended: the layout above is what the base kernels were validated with)
+  double force[3];     // ForcedCollision / ExactDifference body force
+  double smagorinsky;  // SmagorinskyLESBGK coefficient
 };
 
 // ---- explicit global-space memory instructions (SASS: LDG / STG; the compiler cannot prove the address space of
@@ -157,7 +160,17 @@ XLBN_DEV void gstore(T* p, const Pack<T, V>& x) {
 
 // FAST (reciprocal-based) divisions where the kernel is issue-bound: single-precision KBC.  fp64 and BGK keep IEEE division.
 template <int COLL, class TC>
-constexpr bool kFast = (COLL == XLBN_KBC) && (sizeof(TC) == 4);
+constexpr bool kFast = (kBaseCollision<COLL> == XLBN_KBC) && (sizeof(TC) == 4);
+
+// BGK / KBC take the two-argument form they were tuned and validated with; SmagorinskyLESBGK and every forced operator
+// read their extra constants from the parameter block.
+template <int COLL>
+constexpr bool kExtCollision = COLL > XLBN_KBC;
+template <class L, int COLL, class TC, class TS>
+XLBN_DEV void collide_in_step(const StepParams<TS>& p, TC (&f)[L::Q], TC omega) {
+  if constexpr (kExtCollision<COLL>) collide_cell_ext<L, COLL, TC, kFast<COLL, TC>>(f, omega, p.force, p.smagorinsky);
+  else collide_cell<L, COLL, TC, kFast<COLL, TC>>(f, omega);
+}
 
 // f0[l] at an arbitrary (possibly out-of-range) kernel-coordinate cell: periodic in y/z; x through ghost or wrap.
 template <class L, class TC, class TS>
@@ -228,12 +241,12 @@ __device__ __noinline__ void bc_cell(const StepParams<TS>& p, int id, int x, int
         aux[l] = (TC(1.0) - cs) * f[l] + cs * fn;
       }
     XLBN_END
-    collide_cell<L, COLL, TC, kFast<COLL, TC>>(f, omega);
+    collide_in_step<L, COLL, TC, TS>(p, f, omega);
     XLBN_FOR(Q, l)
       if ((miss >> l) & 1u) f[L::opp(l)] = aux[l];
     XLBN_END
   } else {
-    collide_cell<L, COLL, TC, kFast<COLL, TC>>(f, omega);
+    collide_in_step<L, COLL, TC, TS>(p, f, omega);
   }
   XLBN_FOR(Q, l) fio[l] = f[l]; XLBN_END
 }
@@ -257,8 +270,9 @@ struct StepTraits {
   // V*Q population registers (x2 for fp64) + collision temporaries + addresses.
   static constexpr int kW = (int)(sizeof(TC) / 4);
   static constexpr int kRegs = MODE == 2 ? L::Q + 45  // populations stay packed as half2: q registers for two cells
-                               : PK      ? V * L::Q + (COLL == XLBN_KBC ? 4 : 2) * L::Q + 29  // pair temporaries take two registers each
-                                         : V * L::Q * kW + (COLL == XLBN_KBC ? L::Q * kW + 24 : 24) + 5;
+                               : PK      ? V * L::Q + (kBaseCollision<COLL> == XLBN_KBC ? 4 : 2) * L::Q + 29  // pair temporaries take two registers each
+                                         : V * L::Q * kW + (kBaseCollision<COLL> == XLBN_KBC ? L::Q * kW + 24 : 24) + (kForcedCollision<COLL> ? 8 * kW : 0) +
+                                               (kBaseCollision<COLL> == XLBN_SMAGORINSKY_LES_BGK ? 8 * kW : 0) + 5;
   static constexpr int kMinBlocksRaw = 65536 / (kThreads * (kRegs > 255 ? 255 : kRegs));
   static constexpr int kMinBlocksAuto = kMinBlocksRaw < 1 ? 1 : (kMinBlocksRaw > 12 ? 12 : kMinBlocksRaw);
   static constexpr int kMinBlocks = XLBN_MINB_OVERRIDE > 0 ? XLBN_MINB_OVERRIDE : kMinBlocksAuto;
@@ -320,7 +334,7 @@ XLBN_DEV void bc_tail(const StepParams<TS>& p, const Pack<uint8_t, V>& ids, cons
       kind = XLBN_BC_NONE;
     }
     if (kind == XLBN_BC_NONE) {
-      collide_cell<L, COLL, TC, kFast<COLL, TC>>(f[v], omega);
+      collide_in_step<L, COLL, TC, TS>(p, f[v], omega);
     } else if (kind == XLBN_BC_FULLWAY_BOUNCE_BACK) {
       TC t[Q];
       XLBN_FOR(Q, l) t[l] = f[v][L::opp(l)]; XLBN_END
@@ -400,7 +414,7 @@ XLBN_DEV void step_body(const StepParams<TS>& p, const int x, const int y, const
     // straight-line path: no boundary cell among this thread's V cells (ends here, so that its register allocation is
     // independent of the boundary code)
 #pragma unroll
-    for (int v = 0; v < V; ++v) collide_cell<L, COLL, TC, kFast<COLL, TC>>(f[v], omega);
+    for (int v = 0; v < V; ++v) collide_in_step<L, COLL, TC, TS>(p, f[v], omega);
     store_cells<L, TC, TS, V, XC, false>(p, cell, ids, f);
     return;
   }
@@ -728,8 +742,8 @@ inline int pick_cells_per_thread(int requested, int dflt, int esize, int nz, con
 // path (fp32 compute only); 202 = half2-state pair path (FP32FP16 BGK only: the two cells' populations stay packed as
 // half2 registers and are converted on the fly, once for the moments and once for the relaxation).
 template <class L, int COLL, class TC, class TS>
-int launch_step(const StepParams<TS>& p, int x_count, int requested_v, const void* f0, const void* f1, const void* g0, const void* g1,
-                const void* o0, const void* o1, BcEntry* table_rw, double* eq_omega_state, cudaStream_t stream) {
+int launch_step_base(const StepParams<TS>& p, int x_count, int requested_v, const void* f0, const void* f1, const void* g0, const void* g1,
+                     const void* o0, const void* o1, BcEntry* table_rw, double* eq_omega_state, cudaStream_t stream) {
   constexpr bool can_pack = sizeof(TC) == 4 && sizeof(TS) <= 4;
   // defaults selected on B200 (profiles/)
   int req = requested_v;
@@ -768,6 +782,15 @@ int launch_step(const StepParams<TS>& p, int x_count, int requested_v, const voi
   }
 }
 
+// Extended collision models (SmagorinskyLESBGK, forced operators): the one-cell-per-thread scalar kernel only — the
+// layout that won every comparison for the base operators; cells_per_thread is ignored.
+template <class L, int COLL, class TC, class TS>
+int launch_step(const StepParams<TS>& p, int x_count, int requested_v, const void* f0, const void* f1, const void* g0, const void* g1,
+                const void* o0, const void* o1, BcEntry* table_rw, double* eq_omega_state, cudaStream_t stream) {
+  if constexpr (kExtCollision<COLL>) return launch_step_v<L, COLL, TC, TS, 1>(p, x_count, stream);
+  else return launch_step_base<L, COLL, TC, TS>(p, x_count, requested_v, f0, f1, g0, g1, o0, o1, table_rw, eq_omega_state, stream);
+}
+
 // One entry per (lattice, collision); dispatches on (compute, store) dtype.  Defined in step_inst_*.cu.
 struct StepCall {
   int compute_dtype, store_dtype, requested_v;
@@ -786,6 +809,8 @@ struct StepCall {
   void* out_lo;
   void* out_hi;
   cudaStream_t stream;
+  double force[3];  // extended collision models only
+  double smagorinsky;
 };
 
 template <class L, int COLL>
@@ -836,6 +861,8 @@ int run_step_typed(const StepCall& c) {
   p.plane = plane;
   p.n = n;
   p.omega = c.omega;
+  for (int a = 0; a < 3; ++a) p.force[a] = c.force[a];
+  p.smagorinsky = c.smagorinsky;
   return launch_step<L, COLL, TC, TS>(p, c.x_count, c.requested_v, c.f0, c.f1, c.ghost_lo, c.ghost_hi, c.out_lo, c.out_hi, c.table_rw, c.eq_omega_state, c.stream);
 }
 

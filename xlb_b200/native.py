@@ -21,7 +21,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 # enums of include/xlb_b200.h
 D2Q9, D3Q19, D3Q27 = 0, 1, 2
 F16, F32, F64, U8, BOOL = 0, 1, 2, 3, 4
-BGK, KBC = 0, 1
+BGK, KBC, SMAGORINSKY_LES_BGK, COLLISION_FORCED = 0, 1, 2, 4
 MASK_WARP, MASK_JAX = 0, 1
 (
     BC_NONE,
@@ -77,6 +77,8 @@ SIGNATURES = {
     "xlbn_lattice_tables": [_I, _P, _P, _P],
     "xlbn_stepper_create": [C.POINTER(StepperDesc), C.POINTER(_P)],
     "xlbn_stepper_destroy": [_P],
+    "xlbn_stepper_set_force": [_P, C.POINTER(C.c_double)],
+    "xlbn_stepper_set_smagorinsky": [_P, _D],
     "xlbn_step": [_P, _P, _P, _P, _P, C.POINTER(Domain), _D, _I, _P, _P],
     "xlbn_mask_indices": [_I, _I, _P, _LL, _I, _I, Int3, Int3, Int3, _P, _P, _P, _P],
     "xlbn_mask_finalize_jax": [_I, Int3, Int3, Int3, _P, _P, _P],
@@ -87,6 +89,8 @@ SIGNATURES = {
     "xlbn_first_moment": [_I, _I, _P, _I, _P, _I, _P, _I, Int3, _P],
     "xlbn_second_moment": [_I, _I, _P, _I, _P, _I, Int3, _P],
     "xlbn_collide": [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _D, Int3, _P],
+    "xlbn_collide_ext": [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _D, C.POINTER(C.c_double), _D, Int3, _P],
+    "xlbn_exact_difference": [_I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _I, C.POINTER(C.c_double), Int3, _P],
     "xlbn_bc_apply": [_I, _I, C.POINTER(BcDesc), _P, _P, _I, _P, _P, Int3, _P],
     "xlbn_momentum_transfer": [_I, _I, C.POINTER(BcDesc), _P, _P, _I, _P, _P, Int3, _P, _P],
     "xlbn_halo_create": [_I, _I, _I, _I, C.POINTER(_P)],

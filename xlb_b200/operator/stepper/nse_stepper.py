@@ -24,7 +24,7 @@ from xlb_b200.helper.check_boundary_overlaps import check_bc_overlaps
 from xlb_b200.helper.nse_solver import create_nse_fields
 from xlb_b200.operator.boundary_condition.boundary_condition import ImplementationStep
 from xlb_b200.operator.boundary_masker import IndicesBoundaryMasker
-from xlb_b200.operator.collision import BGK, KBC
+from xlb_b200.operator.collision import BGK, KBC, ForcedCollision, SmagorinskyLESBGK
 from xlb_b200.operator.equilibrium import QuadraticEquilibrium
 from xlb_b200.operator.macroscopic import Macroscopic
 from xlb_b200.operator.operator import Operator
@@ -48,10 +48,12 @@ class IncompressibleNavierStokesStepper(Stepper):
             self.collision = BGK(self.velocity_set, self.precision_policy, self.compute_backend)
         elif collision_type == "KBC":
             self.collision = KBC(self.velocity_set, self.precision_policy, self.compute_backend)
+        elif collision_type == "SmagorinskyLESBGK":
+            self.collision = SmagorinskyLESBGK(self.velocity_set, self.precision_policy, self.compute_backend)
         else:
-            raise NotImplementedError(f"collision_type = {collision_type!r} is outside the scope of this backend (BGK, KBC)")
-        if force_vector is not None:
-            raise NotImplementedError("body forces (ForcedCollision / ExactDifference) are outside the scope of this backend")
+            raise NotImplementedError(f"collision_type = {collision_type!r}: the reference has BGK, KBC and SmagorinskyLESBGK (nse_stepper.py:38-43)")
+        if force_vector is not None:  # nse_stepper.py:45-46
+            self.collision = ForcedCollision(collision_operator=self.collision, forcing_scheme=forcing_scheme, force_vector=force_vector)
         self.collision_type = collision_type
         self.streaming_scheme = streaming_scheme
         if streaming_scheme != "pull":
@@ -124,7 +126,9 @@ class IncompressibleNavierStokesStepper(Stepper):
     # -- native handle ---------------------------------------------------------------------------------------------------
     def _native_handle(self):
         descs = [bc.native_desc() for bc in self.boundary_conditions]
-        key = tuple((d.id, d.kind, d.rho, d.u[0], d.u[1], d.u[2]) for d in descs) + (self.cells_per_thread,)
+        coll = self.collision.native_collision
+        force = self.collision.native_force
+        key = tuple((d.id, d.kind, d.rho, d.u[0], d.u[1], d.u[2]) for d in descs) + (self.cells_per_thread, coll, self.collision.native_smagorinsky)
         if self._handle is not None and key == self._handle_key:
             return self._handle
         if self._handle is not None:
@@ -133,7 +137,7 @@ class IncompressibleNavierStokesStepper(Stepper):
         arr = (native.BcDesc * max(1, len(descs)))(*descs)
         desc = native.StepperDesc(
             lattice=self._lattice,
-            collision=self.collision.native_collision,
+            collision=coll & ~native.COLLISION_FORCED,
             compute_dtype=self.precision_policy.compute_precision.code,
             store_dtype=self.precision_policy.store_precision.code,
             n_bc=len(descs),
@@ -143,6 +147,10 @@ class IncompressibleNavierStokesStepper(Stepper):
         out = C.c_void_p()
         native.check(native.lib().xlbn_stepper_create(C.byref(desc), C.byref(out)))
         self._handle, self._handle_key = out, key
+        if coll & ~native.COLLISION_FORCED == native.SMAGORINSKY_LES_BGK:
+            native.check(native.lib().xlbn_stepper_set_smagorinsky(out, float(self.collision.native_smagorinsky)))
+        if force is not None:
+            native.check(native.lib().xlbn_stepper_set_force(out, force))
         self._needs_missing = any(d.kind in (native.BC_HALFWAY_BOUNCE_BACK,) or d.kind >= native.BC_ZOUHE_VELOCITY for d in descs)
         return self._handle
 
