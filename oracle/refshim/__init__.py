@@ -4,13 +4,15 @@ The reference (Autodesk/XLB, /root/reference) is 100 % Python but imports `jax` 
 neither is installed or installable in the build container (no network, no wheel).  All LBM arithmetic of the
 reference's JAX backend is written out in the reference's own files as array expressions (`jnp.roll`, `jnp.where`,
 `jnp.tensordot`, `x.at[i].set(v)` ...).  This package provides *only those array primitives*, backed by numpy and
-following JAX's dtype rules (float32 default, python scalars are weakly typed, int (+) float32 -> float32), plus inert
-placeholders for everything Warp-related (the Warp kernels are never executed — they need the real Warp compiler).
+following JAX's dtype rules (float32 default, python scalars are weakly typed, int (+) float32 -> float32), plus two
+flavours of `warp`: inert placeholders (default; enough to import the package and run the JAX backend), or — with
+`install(interpret_warp=True)` — an INTERPRETIVE stand-in that executes the reference's Warp kernels and functionals
+as the plain Python they are, cell by cell (see `_make_warp_interp`), so that `ComputeBackend.WARP` operators run too.
 
 `install()` puts the stand-ins into `sys.modules`; afterwards `import xlb` (with /root/reference on sys.path) works and
-`ComputeBackend.JAX` operators execute the reference's code line by line.  Used exclusively by
-tests/golden/make_golden.py to generate golden vectors (committed as .npz) and by tests that are skipped when
-/root/reference is absent.  Nothing in the product path imports this.
+the reference's operators execute its own code line by line.  Used exclusively by tests/golden/make_golden.py and
+make_golden_warp.py to generate golden vectors (committed as .npz) and by tests that are skipped when /root/reference is
+absent.  Nothing in the product path imports this.
 """
 
 from __future__ import annotations
