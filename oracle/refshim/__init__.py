@@ -465,7 +465,9 @@ def _make_warp_interp():
     wp.launch = launch
 
     def _as_array(a, dtype=None):
-        return np.array(a, dtype=dtype, copy=True).view(WpArray)
+        if isinstance(dtype, type) and issubclass(dtype, _VecBase):  # array of vectors: trailing axis = components
+            return np.array(a, dtype=dtype._scalar, copy=True).reshape(-1, dtype._length).view(WpArray)
+        return np.array(a, dtype=int if dtype is int else dtype, copy=True).view(WpArray)
 
     wp.array = lambda data=None, dtype=None, **k: None if data is None else _as_array(data, dtype)
     wp.from_numpy = lambda data, dtype=None, **k: _as_array(data, dtype)
@@ -503,6 +505,52 @@ def _make_warp_interp():
     wp.length = lambda a: np.sqrt((a * a).sum(dtype=a.dtype))
     wp.cw_div = lambda a, b: a / b
     wp.cw_mul = lambda a, b: a * b
+    # ---- 3x3 matrices and triangle meshes (mesh_boundary_masker.py) --------------------------------------------------
+    def mat33(*args):
+        """wp.mat33(s) = filled with s; wp.mat33(a, b, c) with three vectors = the vectors as COLUMNS (Warp's convention,
+        which is why the reference transposes the result to index vertices / edges by row)."""
+        if len(args) == 1 and np.ndim(args[0]) == 0:
+            return np.full((3, 3), args[0], dtype=np.float32)
+        if len(args) == 3:
+            return np.stack([np.asarray(a, dtype=np.float32) for a in args], axis=1)
+        return np.asarray(args, dtype=np.float32).reshape(3, 3)
+
+    wp.mat33 = wp.mat33f = mat33
+    wp.transpose = lambda m: np.array(m.T, copy=True)
+    wp.uint64 = np.uint64
+    meshes = {}
+
+    class Mesh:
+        """wp.Mesh: points + flat triangle index list.  Queries are brute force over per-triangle bounding boxes."""
+
+        def __init__(self, points, indices, **k):
+            self.points = np.asarray(points, dtype=np.float32).reshape(-1, 3)
+            self.tris = np.asarray(indices, dtype=np.int64).reshape(-1, 3)
+            corners = self.points[self.tris]
+            self.lo, self.hi = corners.min(axis=1), corners.max(axis=1)
+            self.id = np.uint64(len(meshes) + 1)
+            meshes[int(self.id)] = self
+
+    wp.Mesh = Mesh
+
+    def mesh_query_aabb(mesh_id, lower, upper):  # faces whose bounding box overlaps [lower, upper] (inclusive, as Warp's BVH)
+        m = meshes[int(mesh_id)]
+        hit = np.all(m.lo <= np.asarray(upper), axis=1) & np.all(m.hi >= np.asarray(lower), axis=1)
+        return [int(i) for i in np.nonzero(hit)[0]]
+
+    def mesh_eval_position(mesh_id, face, u, v):  # p*u + q*v + r*(1-u-v)
+        m = meshes[int(mesh_id)]
+        p, q, r = (m.points[i] for i in m.tris[face])
+        return (p * np.float32(u) + q * np.float32(v) + r * np.float32(1.0 - u - v)).view(wp.vec3)
+
+    def mesh_eval_face_normal(mesh_id, face):  # normalize(cross(q - p, r - p))
+        m = meshes[int(mesh_id)]
+        p, q, r = (m.points[i] for i in m.tris[face])
+        n = np.cross(q - p, r - p).astype(np.float32)
+        length = np.sqrt((n * n).sum(dtype=np.float32))
+        return ((n / length) if length > 0 else np.zeros(3, np.float32)).view(wp.vec3)
+
+    wp.mesh_query_aabb, wp.mesh_eval_position, wp.mesh_eval_face_normal = mesh_query_aabb, mesh_eval_position, mesh_eval_face_normal
     utils = _Permissive("warp.utils")
     wp.utils = utils
     return wp, utils

@@ -107,7 +107,7 @@ struct IC {
   __host__ __device__ constexpr operator int() const { return I; }
 };
 template <int N, int I = 0, class F>
-__device__ __forceinline__ void static_for(F&& fn) {
+XLBN_MATH void static_for(F&& fn) {
   if constexpr (I < N) {
     fn(IC<I>{});
     static_for<N, I + 1>(fn);

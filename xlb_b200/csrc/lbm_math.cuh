@@ -7,7 +7,7 @@
 
 namespace xlbn {
 
-#define XLBN_DEV __device__ __forceinline__
+#define XLBN_DEV XLBN_MATH
 #define XLBN_FOR(N, var) static_for<N>([&](auto var##_) { constexpr int var = decltype(var##_)::value;
 #define XLBN_END });
 
@@ -168,8 +168,8 @@ constexpr int kBaseCollision = COLL & 3;
 template <int COLL>
 constexpr bool kForcedCollision = (COLL & XLBN_COLLISION_FORCED) != 0;
 
-__device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
-__device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+XLBN_MATH float sqrt_(float x) { return sqrtf(x); }
+XLBN_MATH double sqrt_(double x) { return sqrt(x); }
 
 // SmagorinskyLESBGK (reference: smagorinsky_les_bgk.py:37-90; a Warp functional only, which reads c[2, l]: 3-D lattices).
 // Restated literally: the 'strain' is a sum of squared non-equilibrium populations selected by the SIGNED component
