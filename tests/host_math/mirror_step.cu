@@ -1,0 +1,140 @@
+// TEST HARNESS — the fused step's SOURCE (xlb_b200/csrc/step_kernel.cuh: fill_step_params, step_body, bc_tail, bc_cell,
+// store_cells and the cell algebra they inline) compiled for the HOST and driven by plain loops instead of a CUDA launch.
+// The loops below do what step_kernel's prologue does (thread coordinates -> x, y, z0; x-plane class); everything else —
+// pointer tables, pull addressing incl. periodic wrap and ghost planes, boundary dispatch, collision, stores incl. the
+// peer-plane stores — is the shipped code.  Not covered: the packed-pair / half2 paths (device intrinsics), launch
+// geometry, and anything that only exists on a GPU (coalescing, races).
+// Built by tests/test_host_mirror_step.py: one object per lattice (-DMIRROR_LATTICE=0|1|2, compiled in parallel) + error.cu,
+// linked into tests/host_math/_build/libmirror_step.so.
+#define XLBN_HOST_MIRROR 1
+#ifndef MIRROR_LATTICE
+#error "compile with -DMIRROR_LATTICE=0 (D2Q9), 1 (D3Q19), 2 (D3Q27 BGK/KBC) or 3 (D3Q27 extended operators)"
+#endif
+#include "../../xlb_b200/csrc/step_kernel.cuh"
+
+using namespace xlbn;
+
+namespace {
+
+template <class L, int COLL, class TC, class TS, int V>
+int host_step(const StepCall& c) {
+  StepParams<TS> p;
+  if (int e = fill_step_params<L, TS>(c, p)) return e;
+  if (c.nz % V) return fail(XLBN_E_SHAPE, "mirror: nz %% V != 0");
+  for (int x = c.x_begin; x < c.x_begin + c.x_count; ++x) {
+    const bool first = (x == 0), last = (x == p.nx - 1);  // as step_kernel
+    for (int y = 0; y < p.ny; ++y)
+      for (int z0 = 0; z0 < p.nz; z0 += V) {
+        if (!first && !last) step_body<L, COLL, TC, TS, V, 0>(p, x, y, z0);
+        else if (first && !last) step_body<L, COLL, TC, TS, V, 1>(p, x, y, z0);
+        else if (last && !first) step_body<L, COLL, TC, TS, V, 2>(p, x, y, z0);
+        else step_body<L, COLL, TC, TS, V, 3>(p, x, y, z0);
+      }
+  }
+  return 0;
+}
+
+template <class L, int COLL, class TC, class TS>
+int host_step_v(const StepCall& c) {
+  if (c.requested_v == 1) return host_step<L, COLL, TC, TS, 1>(c);
+  if constexpr (!kExtCollision<COLL>) {  // the library builds the extended operators with one cell per thread only
+    if (c.requested_v == 2) return host_step<L, COLL, TC, TS, 2>(c);
+    if constexpr (sizeof(TS) <= 4)
+      if (c.requested_v == 4) return host_step<L, COLL, TC, TS, 4>(c);
+  }
+  return fail(XLBN_E_ARG, "mirror: cells per thread %d", c.requested_v);
+}
+
+template <class L, int COLL>
+int host_step_policy(const StepCall& c) {
+  if (c.compute_dtype == XLBN_F32 && c.store_dtype == XLBN_F32) return host_step_v<L, COLL, float, float>(c);
+  if (c.compute_dtype == XLBN_F32 && c.store_dtype == XLBN_F16) return host_step_v<L, COLL, float, __half>(c);
+  if (c.compute_dtype == XLBN_F64 && c.store_dtype == XLBN_F64) return host_step_v<L, COLL, double, double>(c);
+  if (c.compute_dtype == XLBN_F64 && c.store_dtype == XLBN_F32) return host_step_v<L, COLL, double, float>(c);
+  if (c.compute_dtype == XLBN_F64 && c.store_dtype == XLBN_F16) return host_step_v<L, COLL, double, __half>(c);
+  return fail(XLBN_E_DTYPE, "mirror: policy");
+}
+
+}  // namespace
+
+extern "C" {
+
+#if MIRROR_LATTICE == 0
+const char* mirror_last_error(void) { return error_buffer(); }
+#define MIRROR_STEP mirror_step_d2q9
+#elif MIRROR_LATTICE == 1
+#define MIRROR_STEP mirror_step_d3q19
+#elif MIRROR_LATTICE == 2
+#define MIRROR_STEP mirror_step_d3q27
+#else
+#define MIRROR_STEP mirror_step_d3q27_ext
+#endif
+
+// One step of the fused kernel's source on the host.  Arguments as xlbn_step + xlbn_stepper_desc, flattened; all pointers are
+// HOST pointers.  dims are the KERNEL extents (2-D: (1, nx, ny), as xlbn_step passes them).  bc_kind / bc_rho / bc_u: 256-entry
+// tables indexed by bc id.  ghost_* / out_*: x-slab ghost planes as in xlbn_step's halo (NULL: periodic in x).
+int MIRROR_STEP(int lattice, int collision, int compute_dtype, int store_dtype, int cells_per_thread, const void* f0, void* f1, const uint8_t* bc_mask,
+                const uint32_t* missing_bits, const int32_t* bc_kind, const double* bc_rho, const double* bc_u, const int32_t dims[3], int x_begin,
+                int x_count, double omega, const double* force, double smagorinsky, const void* ghost_lo, const void* ghost_hi, void* out_lo,
+                void* out_hi) {
+  static BcEntry table[256];
+  uint8_t kinds[256];
+  memset(table, 0, sizeof(table));
+  for (int i = 0; i < 256; ++i) {
+    table[i].kind = bc_kind[i];
+    table[i].rho = bc_rho[i];
+    for (int a = 0; a < 3; ++a) table[i].u[a] = bc_u[i * 3 + a];
+    kinds[i] = (uint8_t)bc_kind[i];
+  }
+  StepCall c;
+  memset(&c, 0, sizeof(c));
+  c.compute_dtype = compute_dtype;
+  c.store_dtype = store_dtype;
+  c.requested_v = cells_per_thread;
+  c.f0 = f0;
+  c.f1 = f1;
+  c.bc = bc_mask;
+  c.miss = missing_bits;
+  c.table = table;
+  c.table_rw = table;
+  c.eq_omega_state = nullptr;
+  c.kinds = kinds;
+  c.nx = dims[0];
+  c.ny = dims[1];
+  c.nz = dims[2];
+  c.x_begin = x_begin;
+  c.x_count = x_count;
+  c.omega = omega;
+  c.ghost_lo = ghost_lo;
+  c.ghost_hi = ghost_hi;
+  c.out_lo = out_lo;
+  c.out_hi = out_hi;
+  for (int a = 0; a < 3; ++a) c.force[a] = force ? force[a] : 0.0;
+  c.smagorinsky = smagorinsky;
+  constexpr int F = XLBN_COLLISION_FORCED;
+#define CASE(LAT, TAG, COLL) \
+  if (lattice == TAG && collision == (COLL)) return host_step_policy<LAT, (COLL)>(c);
+#if MIRROR_LATTICE == 1
+  CASE(D3Q19, XLBN_D3Q19, XLBN_BGK)
+  CASE(D3Q19, XLBN_D3Q19, XLBN_BGK | F)
+  CASE(D3Q19, XLBN_D3Q19, XLBN_SMAGORINSKY_LES_BGK)
+  CASE(D3Q19, XLBN_D3Q19, XLBN_SMAGORINSKY_LES_BGK | F)
+#elif MIRROR_LATTICE == 2
+  CASE(D3Q27, XLBN_D3Q27, XLBN_BGK)
+  CASE(D3Q27, XLBN_D3Q27, XLBN_KBC)
+#elif MIRROR_LATTICE == 3
+  CASE(D3Q27, XLBN_D3Q27, XLBN_BGK | F)
+  CASE(D3Q27, XLBN_D3Q27, XLBN_KBC | F)
+  CASE(D3Q27, XLBN_D3Q27, XLBN_SMAGORINSKY_LES_BGK)
+  CASE(D3Q27, XLBN_D3Q27, XLBN_SMAGORINSKY_LES_BGK | F)
+#else
+  CASE(D2Q9, XLBN_D2Q9, XLBN_BGK)
+  CASE(D2Q9, XLBN_D2Q9, XLBN_KBC)
+  CASE(D2Q9, XLBN_D2Q9, XLBN_BGK | F)
+  CASE(D2Q9, XLBN_D2Q9, XLBN_KBC | F)
+#endif
+#undef CASE
+  return fail(XLBN_E_ARG, "mirror: lattice %d / collision %d is not built", lattice, collision);
+}
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+"""The fused step kernel's SOURCE, compiled for the host (tests/host_math/mirror_step.cu, -DXLBN_HOST_MIRROR) and driven by
+plain loops, against the reference vectors — both the JAX-backend ones and the WARP-backend ones — on the CPU.
+
+Everything except the launch itself is the shipped code: `fill_step_params` (pointer tables, periodic wrap, ghost
+planes), `step_body` (pull addressing, V cells per thread, x-plane classes), `bc_tail` / `bc_cell` (boundary dispatch, aux
+recovery), the collision incl. the extended operators, `store_cells`.  This is what stands in for a GPU run of the code
+written after the round's GPU budget was spent, and it re-checks the validated kernels on new vectors.
+Tolerances are the GPU tests' (tests/common.py:RTOL)."""
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import EXTRA_CASES_2D, RTOL, STEP_CASES, WARP_CASES, WARP_CASES_N4, load_golden, oracle_masks, rel_err
+from oracle import lbm_c
+from oracle import lbm_numpy as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "host_math", "mirror_step.cu")
+OUT = os.path.join(HERE, "host_math", "_build", "libmirror_step.so")
+CSRC = os.path.join(ROOT, "xlb_b200", "csrc")
+LATTICE = {"D2Q9": 0, "D3Q19": 1, "D3Q27": 2}
+COLLISION = {"BGK": 0, "KBC": 1, "SmagorinskyLESBGK": 2}
+DTYPE = {np.dtype(np.float16): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}
+
+
+@pytest.fixture(scope="module")
+def mirror():
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not available")
+    deps = [SRC] + [os.path.join(CSRC, h) for h in ("step_kernel.cuh", "lbm_math.cuh", "lattice.cuh", "common.cuh", "error.cu")]
+    if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(d) for d in deps):
+        build = os.path.dirname(OUT)
+        os.makedirs(build, exist_ok=True)
+        base = ["nvcc", "-std=c++17", "-O0", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
+        jobs = [(base + ["-c", os.path.join(CSRC, "error.cu"), "-o", os.path.join(build, "error.o")])]
+        jobs += [base + [f"-DMIRROR_LATTICE={k}", "-c", SRC, "-o", os.path.join(build, f"mirror_step_{k}.o")] for k in range(4)]
+        procs = [subprocess.Popen(j, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for j in jobs]  # one object per lattice, in parallel
+        for p in procs:
+            log = p.communicate()[0]
+            assert p.returncode == 0, log[-3000:]
+        objs = [os.path.join(build, "error.o")] + [os.path.join(build, f"mirror_step_{k}.o") for k in range(4)]
+        proc = subprocess.run(["nvcc", "-shared", "-o", OUT] + objs, capture_output=True, text=True)
+        assert proc.returncode == 0, proc.stderr[-3000:]
+    lib = C.CDLL(OUT)
+    lib.mirror_last_error.restype = C.c_char_p
+    P, I, D = C.c_void_p, C.c_int, C.c_double
+    for name in ("mirror_step_d2q9", "mirror_step_d3q19", "mirror_step_d3q27", "mirror_step_d3q27_ext"):
+        getattr(lib, name).argtypes = [I, I, I, I, I, P, P, P, P, P, P, P, P, I, I, D, P, D, P, P, P, P]
+    return lib
+
+
+def mirror_run(lib, g, steps=None, v=1):
+    """The user loop (step, swap) through the host-compiled kernel source; masks and aux data from the oracle helpers."""
+    lat, bcs, bc_mask, missing = oracle_masks(g, "warp")
+    cdt, sdt = O.policy_dtypes(g["policy"])
+    fa = np.ascontiguousarray(g["f_init"], dtype=sdt).copy()
+    fb = fa.copy()
+    lbm_c.write_aux(fb, bcs, bc_mask, missing, lat, g["policy"])  # aux_data_init (boundary_condition.py:119-175): prescribed scalar into f_1[0]
+    desc = lbm_c.make_desc(lat, g["shape"], g["policy"], g["collision"], g["omega"], bcs)
+    kind = np.array(list(desc.bc_kind), dtype=np.int32)  # the C oracle's kind codes are xlbn_bc_kind's
+    rho = np.array(list(desc.bc_rho), dtype=np.float64)
+    u = np.array(list(desc.bc_u), dtype=np.float64)
+    bits = np.ascontiguousarray(sum(missing[l].astype(np.uint32) << np.uint32(l) for l in range(lat.q)).astype(np.uint32))
+    bm = np.ascontiguousarray(bc_mask[0])
+    shape = g["shape"]
+    dims = (C.c_int32 * 3)(*((1,) + tuple(shape) if lat.d == 2 else tuple(shape)))
+    coll = COLLISION[g["collision"]] | (4 if g["force_vector"] is not None else 0)
+    force = np.zeros(3)
+    if g["force_vector"] is not None:
+        force[: lat.d] = g["force_vector"]
+    for _ in range(g["steps"] if steps is None else steps):
+        fn = getattr(lib, "mirror_step_" + g["lattice"].lower() + ("_ext" if g["lattice"] == "D3Q27" and coll > 1 else ""))
+        rc = fn(LATTICE[g["lattice"]], coll, DTYPE[np.dtype(cdt)], DTYPE[np.dtype(sdt)], v, fa.ctypes.data, fb.ctypes.data, bm.ctypes.data,
+                             bits.ctypes.data, kind.ctypes.data, rho.ctypes.data, u.ctypes.data, C.cast(dims, C.c_void_p), 0, dims[0], g["omega"],
+                             force.ctypes.data, g["smagorinsky"], None, None, None, None)  # fmt: skip
+        assert rc == 0, lib.mirror_last_error().decode()
+        fa, fb = fb, fa
+    return fa
+
+
+def mirror_run_slabs(lib, g, n_slabs, steps):
+    """The same user loop on `n_slabs` x-slabs, each with its own arrays and ghost planes; the kernel source itself moves the
+    outgoing face populations into the neighbours' ghost planes (`out_lo` / `out_hi`), double-buffered by step parity, as
+    xlb_b200/distribute/halo.py arranges it between GPUs.  Returns the re-assembled populations."""
+    lat, bcs, bc_mask, missing = oracle_masks(g, "warp")
+    cdt, sdt = O.policy_dtypes(g["policy"])
+    nx, ny, nz = g["shape"]
+    assert nx % n_slabs == 0
+    h = nx // n_slabs
+    fa = np.ascontiguousarray(g["f_init"], dtype=sdt).copy()
+    fb = fa.copy()
+    lbm_c.write_aux(fb, bcs, bc_mask, missing, lat, g["policy"])
+    desc = lbm_c.make_desc(lat, g["shape"], g["policy"], g["collision"], g["omega"], bcs)
+    kind, rho, u = np.array(list(desc.bc_kind), dtype=np.int32), np.array(list(desc.bc_rho)), np.array(list(desc.bc_u))
+    bits = sum(missing[l].astype(np.uint32) << np.uint32(l) for l in range(lat.q)).astype(np.uint32)
+    sl = [slice(r * h, (r + 1) * h) for r in range(n_slabs)]
+    A = [np.ascontiguousarray(fa[:, s]) for s in sl]
+    B = [np.ascontiguousarray(fb[:, s]) for s in sl]
+    BM = [np.ascontiguousarray(bc_mask[0][s]) for s in sl]
+    BITS = [np.ascontiguousarray(bits[s]) for s in sl]
+    right, left = list(lat.right), list(lat.left)  # c_x = +1 / -1 populations in slot order (lattice.cuh: xdir_slot)
+    # ghosts[rank][parity][side]: side 0 = plane "x = -1" (c_x = +1 populations), side 1 = plane "x = h" (c_x = -1 populations)
+    ghosts = [[[np.zeros((len(right), ny, nz), sdt) for _ in range(2)] for _ in range(2)] for _ in range(n_slabs)]
+    for r in range(n_slabs):  # prime parity 0 from the initial state (halo.py: exchange_ghost_planes)
+        ghosts[r][0][0][...] = A[(r - 1) % n_slabs][right, h - 1]
+        ghosts[r][0][1][...] = A[(r + 1) % n_slabs][left, 0]
+    dims = (C.c_int32 * 3)(h, ny, nz)
+    coll = COLLISION[g["collision"]] | (4 if g["force_vector"] is not None else 0)
+    force = np.zeros(3)
+    if g["force_vector"] is not None:
+        force[: lat.d] = g["force_vector"]
+    fn = getattr(lib, "mirror_step_" + g["lattice"].lower() + ("_ext" if g["lattice"] == "D3Q27" and coll > 1 else ""))
+    for t in range(steps):
+        pin, pout = t & 1, (t + 1) & 1
+        for r in range(n_slabs):
+            hi, lo = (r + 1) % n_slabs, (r - 1) % n_slabs
+            rc = fn(LATTICE[g["lattice"]], coll, DTYPE[np.dtype(cdt)], DTYPE[np.dtype(sdt)], 1, A[r].ctypes.data, B[r].ctypes.data, BM[r].ctypes.data,
+                    BITS[r].ctypes.data, kind.ctypes.data, rho.ctypes.data, u.ctypes.data, C.cast(dims, C.c_void_p), 0, h, g["omega"], force.ctypes.data,
+                    g["smagorinsky"], ghosts[r][pin][0].ctypes.data, ghosts[r][pin][1].ctypes.data, ghosts[lo][pout][1].ctypes.data,
+                    ghosts[hi][pout][0].ctypes.data)  # fmt: skip
+            assert rc == 0, lib.mirror_last_error().decode()
+        A, B = B, A
+    return np.concatenate(A, axis=1)
+
+
+@pytest.mark.parametrize("n_slabs", [2, 4])
+@pytest.mark.parametrize("name", ["warp_tunnel_d3q27_kbc_regularized_outflow", "sphere_d3q19_bgk_zouhe_pressure_fp32", "periodic_d3q19_bgk_fp32", "warp_periodic_d3q27_smagorinsky_forced"])
+def test_slab_decomposition_through_ghost_planes_is_bit_identical(mirror, name, n_slabs):
+    """x-slabs with one ghost plane per side, outgoing face populations stored into the neighbours' ghost planes
+    by the step itself — same bits as the undecomposed run (on the GPU: tests/test_native_slab_gpu.py, scripts/mgpu_check.py)."""
+    g = load_golden(name)
+    if g["shape"][0] % n_slabs:
+        pytest.skip("nx not divisible")
+    assert np.array_equal(mirror_run_slabs(mirror, g, n_slabs, 6), mirror_run(mirror, g, steps=6))
+
+
+def test_bc_kind_codes_agree_with_the_header():
+    """mirror_run hands the C oracle's kind codes to the kernel source: they must be xlbn_bc_kind's."""
+    from xlb_b200 import native
+
+    assert (native.BC_EQUILIBRIUM, native.BC_DO_NOTHING, native.BC_HALFWAY_BOUNCE_BACK, native.BC_FULLWAY_BOUNCE_BACK) == (1, 2, 3, 4)
+    assert lbm_c.KIND == {"equilibrium": 1, "donothing": 2, "halfway": 3, "fullway": 4, "outflow": native.BC_EXTRAPOLATION_OUTFLOW}
+    assert lbm_c._ZOUHE[("zouhe", "velocity")] == native.BC_ZOUHE_VELOCITY and lbm_c._ZOUHE[("regularized", "pressure")] == native.BC_REGULARIZED_PRESSURE
+
+
+@pytest.mark.parametrize("name", STEP_CASES + EXTRA_CASES_2D + WARP_CASES + WARP_CASES_N4)
+def test_kernel_source_on_the_host_matches_the_reference_vectors(mirror, name):
+    g = load_golden(name)
+    f = mirror_run(mirror, g)
+    assert f.dtype == g["f_final"].astype(O.policy_dtypes(g["policy"])[1]).dtype
+    assert rel_err(f, g["f_final"]) <= RTOL[g["policy"]], rel_err(f, g["f_final"])
+
+
+@pytest.mark.parametrize("v", [2, 4])
+@pytest.mark.parametrize("name", ["sphere_d3q27_kbc_fp32", "warp_tunnel_d3q19_bgk_zouhe_pressure", "cavity_d3q19_bgk_fp32fp16", "channel2d_d2q9_bgk_outflow_fp32"])
+def test_cells_per_thread_variants_are_identical_to_one_cell_per_thread(mirror, name, v):
+    g = load_golden(name)
+    if g["shape"][-1] % v:
+        pytest.skip("nz not divisible")
+    assert np.array_equal(mirror_run(mirror, g, steps=8, v=v), mirror_run(mirror, g, steps=8, v=1))

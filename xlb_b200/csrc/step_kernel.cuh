@@ -82,32 +82,58 @@ template <>
 struct GMem<1> {
   using T = uint8_t;
   static XLBN_DEV T ld(const void* p) {
+#if XLBN_ON_HOST
+    return *static_cast<const T*>(p);
+#else
     uint32_t v;
     asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p));
     return (T)v;
+#endif
   }
-  static XLBN_DEV void st(void* p, T v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"((uint32_t)v) : "memory"); }
+  static XLBN_DEV void st(void* p, T v) {
+#if XLBN_ON_HOST
+    *static_cast<T*>(p) = v;
+#else
+    asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"((uint32_t)v) : "memory");
+#endif
+  }
 };
 template <>
 struct GMem<2> {
   using T = uint16_t;
   static XLBN_DEV T ld(const void* p) {
+#if XLBN_ON_HOST
+    return *static_cast<const T*>(p);
+#else
     T v;
     asm volatile("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(p));
     return v;
+#endif
   }
-  static XLBN_DEV void st(void* p, T v) { asm volatile("st.global.u16 [%0], %1;" ::"l"(p), "h"(v) : "memory"); }
+  static XLBN_DEV void st(void* p, T v) {
+#if XLBN_ON_HOST
+    *static_cast<T*>(p) = v;
+#else
+    asm volatile("st.global.u16 [%0], %1;" ::"l"(p), "h"(v) : "memory");
+#endif
+  }
 };
 template <>
 struct GMem<4> {
   using T = uint32_t;
   static XLBN_DEV T ld(const void* p) {
+#if XLBN_ON_HOST
+    return *static_cast<const T*>(p);
+#else
     T v;
     asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
+#endif
   }
   static XLBN_DEV void st(void* p, T v) {
-#if XLBN_ST_CS
+#if XLBN_ON_HOST
+    *static_cast<T*>(p) = v;
+#elif XLBN_ST_CS
     asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 #else
     asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -118,22 +144,40 @@ template <>
 struct GMem<8> {
   using T = uint2;
   static XLBN_DEV T ld(const void* p) {
+#if XLBN_ON_HOST
+    return *static_cast<const T*>(p);
+#else
     T v;
     asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
+#endif
   }
-  static XLBN_DEV void st(void* p, T v) { asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory"); }
+  static XLBN_DEV void st(void* p, T v) {
+#if XLBN_ON_HOST
+    *static_cast<T*>(p) = v;
+#else
+    asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+#endif
+  }
 };
 template <>
 struct GMem<16> {
   using T = uint4;
   static XLBN_DEV T ld(const void* p) {
+#if XLBN_ON_HOST
+    return *static_cast<const T*>(p);
+#else
     T v;
     asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
+#endif
   }
   static XLBN_DEV void st(void* p, T v) {
+#if XLBN_ON_HOST
+    *static_cast<T*>(p) = v;
+#else
     asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#endif
   }
 };
 
@@ -174,7 +218,7 @@ XLBN_DEV void collide_in_step(const StepParams<TS>& p, TC (&f)[L::Q], TC omega) 
 
 // f0[l] at an arbitrary (possibly out-of-range) kernel-coordinate cell: periodic in y/z; x through ghost or wrap.
 template <class L, class TC, class TS>
-__device__ TC load_f0_any(const StepParams<TS>& p, int l, int ck0, int slot, int x, int y, int z) {
+XLBN_DEVFN TC load_f0_any(const StepParams<TS>& p, int l, int ck0, int slot, int x, int y, int z) {
   y = (y % p.ny + p.ny) % p.ny;
   z = (z % p.nz + p.nz) % p.nz;
   const long long yz = (long long)y * p.nz + z;
@@ -188,7 +232,7 @@ __device__ TC load_f0_any(const StepParams<TS>& p, int l, int ck0, int slot, int
 // on exit.  Order of operations = reference kernel: streaming BC -> collide -> collision BC / outflow aux -> aux recovery
 // (nse_stepper.py:361-381).
 template <class L, int COLL, class TC, class TS>
-__device__ __noinline__ void bc_cell(const StepParams<TS>& p, int id, int x, int y, int z, TC* fio) {
+XLBN_DEVFN __noinline__ void bc_cell(const StepParams<TS>& p, int id, int x, int y, int z, TC* fio) {
   constexpr int Q = L::Q;
   TC f[Q];
   XLBN_FOR(Q, l) f[l] = fio[l]; XLBN_END
@@ -423,24 +467,24 @@ XLBN_DEV void step_body(const StepParams<TS>& p, const int x, const int y, const
 
 // ---- packed pair path: two neighbouring cells per fp32x2 register pair (FADD2 / FMUL2 / FFMA2) ---------------------
 template <class TS>
-XLBN_DEV f32x2 pair_up(TS lo, TS hi);
+XLBN_DEVONLY f32x2 pair_up(TS lo, TS hi);
 template <>
-XLBN_DEV f32x2 pair_up<float>(float lo, float hi) { return f32x2(lo, hi); }
+XLBN_DEVONLY f32x2 pair_up<float>(float lo, float hi) { return f32x2(lo, hi); }
 template <>
-XLBN_DEV f32x2 pair_up<__half>(__half lo, __half hi) { return f32x2(__half22float2(__halves2half2(lo, hi))); }
+XLBN_DEVONLY f32x2 pair_up<__half>(__half lo, __half hi) { return f32x2(__half22float2(__halves2half2(lo, hi))); }
 template <class TS>
-XLBN_DEV void pair_down(f32x2 v, TS& lo, TS& hi);
+XLBN_DEVONLY void pair_down(f32x2 v, TS& lo, TS& hi);
 template <>
-XLBN_DEV void pair_down<float>(f32x2 v, float& lo, float& hi) { lo = v.v.x; hi = v.v.y; }
+XLBN_DEVONLY void pair_down<float>(f32x2 v, float& lo, float& hi) { lo = v.v.x; hi = v.v.y; }
 template <>
-XLBN_DEV void pair_down<__half>(f32x2 v, __half& lo, __half& hi) {
+XLBN_DEVONLY void pair_down<__half>(f32x2 v, __half& lo, __half& hi) {
   const __half2 h = __float22half2_rn(v.v);
   lo = __low2half(h);
   hi = __high2half(h);
 }
 
 template <class L, int COLL, class TS, int V, int XC>
-XLBN_DEV void step_body_pk(const StepParams<TS>& p, const int x, const int y, const int z0) {
+XLBN_DEVONLY void step_body_pk(const StepParams<TS>& p, const int x, const int y, const int z0) {
   static_assert(V % 2 == 0, "pair path needs an even number of cells per thread");
   constexpr int Q = L::Q, NP = V / 2;
   const unsigned nz = (unsigned)p.nz;
@@ -531,7 +575,7 @@ __global__ void bc_precompute_kernel(BcEntry* table, float omega) {
 // FullwayBounceBack (bit copy of the opposite population's half; fp16 -> fp32 -> fp16 is exact) and EquilibriumBC cells
 // (the precomputed constant update, BcEntry::eq_out); id_lo / id_hi = bc ids of the two cells.
 template <class L, int XC, bool WITH_BC>
-XLBN_DEV void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L::Q], const unsigned cell, const int id_lo, const int id_hi) {
+XLBN_DEVONLY void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L::Q], const unsigned cell, const int id_lo, const int id_hi) {
   using TS = __half;
   constexpr int Q = L::Q;
   bool eq_lo = false, eq_hi = false, fw_lo = false, fw_hi = false;
@@ -602,7 +646,7 @@ XLBN_DEV void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L
 // so the kernel keeps the residency of the one-cell path while issuing ~2.5x fewer instructions per cell (FADD2 / FMUL2 /
 // FFMA2 for both cells at once); the fp16 path is issue-bound otherwise (profiles/README.md).
 template <class L, int XC>
-XLBN_DEV void step_body_h2(const StepParams<__half>& p, const int x, const int y, const int z0) {
+XLBN_DEVONLY void step_body_h2(const StepParams<__half>& p, const int x, const int y, const int z0) {
   using TS = __half;
   constexpr int Q = L::Q, V = 2;
   const unsigned nz = (unsigned)p.nz;
@@ -816,9 +860,9 @@ struct StepCall {
 template <class L, int COLL>
 int dispatch_step(const StepCall& c);
 
-template <class L, int COLL, class TC, class TS>
-int run_step_typed(const StepCall& c) {
-  StepParams<TS> p;
+// Host: fold everything that depends only on (population, x-plane class) into the kernel's pointer tables.
+template <class L, class TS>
+int fill_step_params(const StepCall& c, StepParams<TS>& p) {
   memset(&p, 0, sizeof(p));
   const TS* f0 = static_cast<const TS*>(c.f0);
   TS* f1 = static_cast<TS*>(c.f1);
@@ -863,6 +907,13 @@ int run_step_typed(const StepCall& c) {
   p.omega = c.omega;
   for (int a = 0; a < 3; ++a) p.force[a] = c.force[a];
   p.smagorinsky = c.smagorinsky;
+  return 0;
+}
+
+template <class L, int COLL, class TC, class TS>
+int run_step_typed(const StepCall& c) {
+  StepParams<TS> p;
+  if (int e = fill_step_params<L, TS>(c, p)) return e;
   return launch_step<L, COLL, TC, TS>(p, c.x_count, c.requested_v, c.f0, c.f1, c.ghost_lo, c.ghost_hi, c.out_lo, c.out_hi, c.table_rw, c.eq_omega_state, c.stream);
 }
 
