@@ -127,11 +127,13 @@ int MIRROR_STEP(int lattice, int collision, int compute_dtype, int store_dtype, 
   CASE(D3Q27, XLBN_D3Q27, XLBN_KBC | F)
   CASE(D3Q27, XLBN_D3Q27, XLBN_SMAGORINSKY_LES_BGK)
   CASE(D3Q27, XLBN_D3Q27, XLBN_SMAGORINSKY_LES_BGK | F)
+  CASE(D3Q27, XLBN_D3Q27, XLBN_KBC | kLeanKbc)
 #else
   CASE(D2Q9, XLBN_D2Q9, XLBN_BGK)
   CASE(D2Q9, XLBN_D2Q9, XLBN_KBC)
   CASE(D2Q9, XLBN_D2Q9, XLBN_BGK | F)
   CASE(D2Q9, XLBN_D2Q9, XLBN_KBC | F)
+  CASE(D2Q9, XLBN_D2Q9, XLBN_KBC | kLeanKbc)
 #endif
 #undef CASE
   return fail(XLBN_E_ARG, "mirror: lattice %d / collision %d is not built", lattice, collision);

@@ -55,7 +55,7 @@ def mirror():
     return lib
 
 
-def mirror_run(lib, g, steps=None, v=1):
+def mirror_run(lib, g, steps=None, v=1, lean_kbc=False):
     """The user loop (step, swap) through the host-compiled kernel source; masks and aux data from the oracle helpers."""
     lat, bcs, bc_mask, missing = oracle_masks(g, "warp")
     cdt, sdt = O.policy_dtypes(g["policy"])
@@ -70,7 +70,7 @@ def mirror_run(lib, g, steps=None, v=1):
     bm = np.ascontiguousarray(bc_mask[0])
     shape = g["shape"]
     dims = (C.c_int32 * 3)(*((1,) + tuple(shape) if lat.d == 2 else tuple(shape)))
-    coll = COLLISION[g["collision"]] | (4 if g["force_vector"] is not None else 0)
+    coll = COLLISION[g["collision"]] | (4 if g["force_vector"] is not None else 0) | (8 if lean_kbc else 0)  # 8: csrc/lbm_math.cuh kLeanKbc
     force = np.zeros(3)
     if g["force_vector"] is not None:
         force[: lat.d] = g["force_vector"]
@@ -138,6 +138,16 @@ def test_slab_decomposition_through_ghost_planes_is_bit_identical(mirror, name, 
     if g["shape"][0] % n_slabs:
         pytest.skip("nx not divisible")
     assert np.array_equal(mirror_run_slabs(mirror, g, n_slabs, 6), mirror_run(mirror, g, steps=6))
+
+
+@pytest.mark.parametrize("name", [n for n in STEP_CASES + WARP_CASES if "kbc" in n])
+def test_lean_kbc_variant_matches_the_reference_vectors(mirror, name):
+    """cells_per_thread = 301: the register-lean arrangement of the KBC collision (a tuning candidate for round 2) holds the
+    same tolerance against the reference and stays within rounding of the default formulation."""
+    g = load_golden(name)
+    lean = mirror_run(mirror, g, lean_kbc=True)
+    assert rel_err(lean, g["f_final"]) <= RTOL[g["policy"]]
+    assert rel_err(lean, mirror_run(mirror, g)) <= 3e-6
 
 
 def test_bc_kind_codes_agree_with_the_header():

@@ -9,7 +9,7 @@ import sys
 
 import pytest
 
-from common import EXTRA_CASES_2D, WARP_CASES, WARP_CASES_N4
+from common import EXTRA_CASES_2D, STEP_CASES, WARP_CASES, WARP_CASES_N4
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -21,7 +21,7 @@ import numpy as np
 from common import load_golden, native_run, rel_err, unpack_bits
 g = load_golden(%(name)r)
 q = g["f_final"].shape[0]
-f, bc_mask, missing = native_run(g, backend=%(backend)r)
+f, bc_mask, missing = native_run(g, backend=%(backend)r, cells_per_thread=%(v)d)
 ok_masks = np.array_equal(bc_mask.reshape(g["bc_mask"].shape), g["bc_mask"]) and np.array_equal(missing.reshape((q,) + g["shape"]), unpack_bits(g["missing_bits"], q))
 print("RESULT", ok_masks, rel_err(f, g["f_final"]))
 if "force" in g:
@@ -36,8 +36,8 @@ if "force" in g:
 """
 
 
-def run_child(name, backend):
-    proc = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT, "name": name, "backend": backend}], capture_output=True, text=True, timeout=300, cwd=ROOT)
+def run_child(name, backend, v=0):
+    proc = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT, "name": name, "backend": backend, "v": v}], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert proc.returncode == 0, proc.stderr[-1500:]
     lines = {l.split()[0]: l.split()[1:] for l in proc.stdout.splitlines() if l.startswith(("RESULT", "FORCE"))}
     assert lines["RESULT"][0] == "True", "masks differ"
@@ -68,6 +68,13 @@ def test_first_run_against_the_reference_warp_backend(name):
 def test_first_run_of_the_extended_collision_kernels(name):
     """SmagorinskyLESBGK / ForcedCollision in the fused step: kernels that have never run on a GPU."""
     run_child(name, "WARP")
+
+
+@LATE
+@pytest.mark.parametrize("name", [n for n in STEP_CASES + WARP_CASES if "kbc" in n])
+def test_first_run_of_the_lean_kbc_variant(name):
+    """cells_per_thread = 301 (register-lean KBC): host-validated, never run on a GPU."""
+    run_child(name, "WARP", v=301)
 
 
 OPS_CHILD = r"""

@@ -36,6 +36,8 @@ template <> int dispatch_step<D3Q27, XLBN_SMAGORINSKY_LES_BGK>(const StepCall&);
 template <> int dispatch_step<D3Q27, XLBN_SMAGORINSKY_LES_BGK | kF>(const StepCall&);
 template <> int dispatch_step<D2Q9, XLBN_BGK | kF>(const StepCall&);
 template <> int dispatch_step<D2Q9, XLBN_KBC | kF>(const StepCall&);
+template <> int dispatch_step<D3Q27, XLBN_KBC | kLeanKbc>(const StepCall&);  // tuning variant (cells_per_thread = 301)
+template <> int dispatch_step<D2Q9, XLBN_KBC | kLeanKbc>(const StepCall&);
 }  // namespace xlbn
 
 extern "C" {
@@ -77,7 +79,9 @@ int xlbn_stepper_create(const xlbn_stepper_desc* desc, xlbn_stepper** out) {
   if (desc->compute_dtype == XLBN_F32 && desc->store_dtype == XLBN_F64) return fail(XLBN_E_DTYPE, "stepper_create: no FP32FP64 policy");
   if (desc->n_bc < 0 || (desc->n_bc > 0 && !desc->bcs)) return fail(XLBN_E_ARG, "stepper_create: bad BC list");
   const int cpt = desc->cells_per_thread;
-  if (cpt != 0 && cpt != 1 && cpt != 2 && cpt != 4 && cpt != 8 && cpt != 102 && cpt != 104 && cpt != 202) return fail(XLBN_E_ARG, "stepper_create: cells_per_thread = %d", cpt);
+  if (cpt != 0 && cpt != 1 && cpt != 2 && cpt != 4 && cpt != 8 && cpt != 102 && cpt != 104 && cpt != 202 && cpt != 301)
+    return fail(XLBN_E_ARG, "stepper_create: cells_per_thread = %d", cpt);
+  if (cpt == 301 && desc->collision != XLBN_KBC) return fail(XLBN_E_ARG, "stepper_create: cells_per_thread = 301 selects the lean KBC collision; the stepper's collision is %d", desc->collision);
 
   BcEntry host[256];
   memset(host, 0, sizeof(host));
@@ -198,7 +202,8 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
     c.out_hi = halo_ghost(halo, halo->peer_hi, p_out, 0);
     c.out_lo = halo_ghost(halo, halo->peer_lo, p_out, 1);
   }
-  const int coll = s->collision | (s->forced ? kF : 0);
+  if (s->cells_per_thread == 301 && s->forced) return fail(XLBN_E_UNSUPPORTED, "xlbn_step: the lean KBC variant (cells_per_thread = 301) has no forced form");
+  const int coll = s->collision | (s->forced ? kF : 0) | (s->cells_per_thread == 301 ? kLeanKbc : 0);
   switch (s->lattice) {
     case XLBN_D3Q19:
       switch (coll) {
@@ -214,6 +219,7 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
         case XLBN_KBC: return dispatch_step<D3Q27, XLBN_KBC>(c);
         case XLBN_BGK | kF: return dispatch_step<D3Q27, XLBN_BGK | kF>(c);
         case XLBN_KBC | kF: return dispatch_step<D3Q27, XLBN_KBC | kF>(c);
+        case XLBN_KBC | kLeanKbc: return dispatch_step<D3Q27, XLBN_KBC | kLeanKbc>(c);
         case XLBN_SMAGORINSKY_LES_BGK: return dispatch_step<D3Q27, XLBN_SMAGORINSKY_LES_BGK>(c);
         case XLBN_SMAGORINSKY_LES_BGK | kF: return dispatch_step<D3Q27, XLBN_SMAGORINSKY_LES_BGK | kF>(c);
       }
@@ -224,6 +230,7 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
         case XLBN_KBC: return dispatch_step<D2Q9, XLBN_KBC>(c);
         case XLBN_BGK | kF: return dispatch_step<D2Q9, XLBN_BGK | kF>(c);
         case XLBN_KBC | kF: return dispatch_step<D2Q9, XLBN_KBC | kF>(c);
+        case XLBN_KBC | kLeanKbc: return dispatch_step<D2Q9, XLBN_KBC | kLeanKbc>(c);
       }
       break;
   }

@@ -201,10 +201,142 @@ XLBN_DEV void exact_difference(TC rho, const TC (&u)[L::D], const TC (&feq)[L::Q
   XLBN_FOR(L::Q, l) out[l] += feq_force[l] - feq[l]; XLBN_END
 }
 
+// ---- KBC, register-lean formulation (tuning variant, opt-in: cells_per_thread = 301) ---------------------------------------
+// Same algebra as collide_kbc with FAST divisions, arranged as three passes over the populations that RECOMPUTE feq_l
+// instead of holding feq[], fneq[], ds[] (3 q-vectors) next to f[]: six distinct shear values instead of a q-vector, the
+// shear-free populations (rest + 8 corners on D3Q27) skipped, and an opaque launder() on (rho, u, usqr) between the passes so
+// that the compiler cannot CSE the recomputation back into q live values.  ptxas, D3Q27 fp32: 72 registers / 32 B spilled
+// against 80 / 1 KiB for collide_kbc, for +9 % instructions (profiles/round2_prep/).  Differs from collide_kbc by rounding
+// only (x/4 -> x*0.25 is exact; the output is f - beta*gamma*fneq - beta*(2-gamma)*ds instead of f - beta*(2 ds + gamma dh)).
+constexpr int kLeanKbc = 8;  // internal flag or-ed onto XLBN_KBC in the COLL template argument
+
+XLBN_DEV void launder(float& x) {
+#if !XLBN_ON_HOST
+  asm volatile("" : "+f"(x));
+#endif
+}
+XLBN_DEV void launder(double& x) {
+#if !XLBN_ON_HOST
+  asm volatile("" : "+d"(x));
+#endif
+}
+
+// one population's equilibrium from (rho, u, usqr)   (quadratic_equilibrium.py:35-60, same expression as equilibrium())
+template <class L, class TC, int l>
+XLBN_DEV TC feq_one(TC rho, const TC (&u)[L::D], TC usqr) {
+  TC cu = TC(0);
+  XLBN_FOR(L::D, d)
+    if constexpr (L::c(d, l) == 1) cu += u[d];
+    else if constexpr (L::c(d, l) == -1) cu -= u[d];
+  XLBN_END
+  cu *= TC(3.0);
+  return rho * TC(L::w(l)) * (fma_(cu, fma_(TC(0.5), cu, TC(1.0)), TC(1.0)) - usqr);
+}
+
+// delta_s of population l from the distinct shear values (already multiplied by rho [/4 in 2-D]); kbc.py:213-250, SURVEY Appendix B
+template <class L, class TC, int l>
+XLBN_DEV TC kbc_ds(const TC (&sv)[6]) {
+  if constexpr (L::ID == XLBN_D3Q27) {
+    if constexpr (l == 9 || l == 18) return sv[0];
+    else if constexpr (l == 3 || l == 6) return sv[1];
+    else if constexpr (l == 1 || l == 2) return sv[2];
+    else if constexpr (l == 12 || l == 24) return sv[3];
+    else if constexpr (l == 21 || l == 15) return -sv[3];
+    else if constexpr (l == 10 || l == 20) return sv[4];
+    else if constexpr (l == 19 || l == 11) return -sv[4];
+    else if constexpr (l == 8 || l == 4) return sv[5];
+    else if constexpr (l == 7 || l == 5) return -sv[5];
+    else return TC(0);
+  } else {
+    if constexpr (l == 3 || l == 6) return sv[0];
+    else if constexpr (l == 1 || l == 2) return -sv[0];
+    else if constexpr (l == 7 || l == 8) return sv[1];
+    else if constexpr (l == 4 || l == 5) return -sv[1];
+    else return TC(0);
+  }
+}
+template <class L, int l>
+__host__ __device__ constexpr bool kbc_has_shear() {
+  if constexpr (L::ID == XLBN_D3Q27) return l != 0 && L::speed(l) != 3;
+  else return l != 0;
+}
+
+template <class L, class TC, bool FAST>
+XLBN_DEV void collide_kbc_lean(TC (&f)[L::Q], TC omega) {
+  static_assert(L::ID == XLBN_D3Q27 || L::ID == XLBN_D2Q9, "KBC: D3Q27 and D2Q9 only (kbc.py:71-72)");
+  TC rho, u[L::D];
+  macroscopic<L, TC, FAST>(f, rho, u);
+  TC uu = u[0] * u[0];
+  XLBN_FOR(L::D - 1, d) uu = fma_(u[d + 1], u[d + 1], uu); XLBN_END
+  TC usqr = TC(1.5) * uu;
+  // pass 1: Pi_neq
+  TC pi[L::NT];
+  XLBN_FOR(L::NT, t) pi[t] = TC(0); XLBN_END
+  XLBN_FOR(L::Q, l)
+    const TC fneq = f[l] - feq_one<L, TC, l>(rho, u, usqr);
+    XLBN_FOR(L::NT, t)
+      if constexpr (L::cc(l, t) == 1) pi[t] += fneq;
+      else if constexpr (L::cc(l, t) == -1) pi[t] -= fneq;
+    XLBN_END
+  XLBN_END
+  TC sv[6];
+  if constexpr (L::ID == XLBN_D3Q27) {
+    const TC nxz = pi[0] - pi[5], nyz = pi[3] - pi[5];
+    sv[0] = (TC(2.0) * nxz - nyz) * TC(1.0 / 6.0) * rho;
+    sv[1] = (-nxz + TC(2.0) * nyz) * TC(1.0 / 6.0) * rho;
+    sv[2] = (-nxz - nyz) * TC(1.0 / 6.0) * rho;
+    sv[3] = pi[1] * TC(0.25) * rho;
+    sv[4] = pi[2] * TC(0.25) * rho;
+    sv[5] = pi[4] * TC(0.25) * rho;
+  } else {
+    sv[0] = (pi[0] - pi[2]) * rho * TC(0.25);
+    sv[1] = pi[1] * rho * TC(0.25);
+    sv[2] = sv[3] = sv[4] = sv[5] = TC(0);
+  }
+  launder(rho);
+  launder(usqr);
+  XLBN_FOR(L::D, d) launder(u[d]); XLBN_END
+  // pass 2: entropic scalar products
+  TC sp1 = TC(0), sp2 = TC(0);
+  XLBN_FOR(L::Q, l)
+    const TC feq = feq_one<L, TC, l>(rho, u, usqr);
+    const TC fneq = f[l] - feq;
+    const TC r = rcp_approx_(feq);
+    if constexpr (kbc_has_shear<L, l>()) {
+      const TC ds = kbc_ds<L, TC, l>(sv);
+      const TC dh = fneq - ds;
+      const TC temp = dh * r;
+      sp1 = fma_(temp, ds, sp1);
+      sp2 = fma_(temp, dh, sp2);
+    } else {
+      sp2 = fma_(fneq * r, fneq, sp2);
+    }
+  XLBN_END
+  const TC beta = TC(0.5) * omega;
+  const TC inv_beta = TC(1.0) / beta;
+  const TC gamma = inv_beta - (TC(2.0) - inv_beta) * sp1 / (TC(1e-32) + sp2);
+  // pass 3: f - beta (2 ds + gamma dh) = f - beta gamma fneq - beta (2 - gamma) ds
+  launder(rho);
+  launder(usqr);
+  XLBN_FOR(L::D, d) launder(u[d]); XLBN_END
+  const TC bg = beta * gamma, b2 = beta * (TC(2.0) - gamma);
+  XLBN_FOR(L::Q, l)
+    const TC fneq = f[l] - feq_one<L, TC, l>(rho, u, usqr);
+    TC out = fma_(-bg, fneq, f[l]);
+    if constexpr (kbc_has_shear<L, l>()) out = fma_(-b2, kbc_ds<L, TC, l>(sv), out);
+    f[l] = out;
+  XLBN_END
+}
+
 // macroscopic -> equilibrium -> collision [-> forcing] on one cell, in place, for every operator incl. the extended ones
 // (reference: nse_stepper.py:369-371 with self.collision = ForcedCollision(...), L45-46).
 template <class L, int COLL, class TC, bool FAST = false>
 XLBN_DEV void collide_cell_ext(TC (&f)[L::Q], TC omega, const double* force, double smagorinsky) {
+  if constexpr ((COLL & kLeanKbc) != 0) {
+    static_assert(kBaseCollision<COLL> == XLBN_KBC && !kForcedCollision<COLL>, "the lean formulation exists for plain KBC only");
+    collide_kbc_lean<L, TC, FAST>(f, omega);
+    return;
+  }
   TC rho, u[L::D], feq[L::Q], out[L::Q];
   macroscopic<L, TC, FAST>(f, rho, u);
   equilibrium<L, TC>(rho, u, feq);

@@ -313,7 +313,8 @@ struct StepTraits {
   // Occupancy-first register budget (the kernel is latency-bound until ~48 warps/SM are resident, profiles/):
   // V*Q population registers (x2 for fp64) + collision temporaries + addresses.
   static constexpr int kW = (int)(sizeof(TC) / 4);
-  static constexpr int kRegs = MODE == 2 ? L::Q + 45  // populations stay packed as half2: q registers for two cells
+  static constexpr int kRegs = (COLL & kLeanKbc) ? (L::Q + 45) * kW  // lean KBC: f[] + (rho, u, usqr, pi / sv, sums) and addresses
+                               : MODE == 2 ? L::Q + 45  // populations stay packed as half2: q registers for two cells
                                : PK      ? V * L::Q + (kBaseCollision<COLL> == XLBN_KBC ? 4 : 2) * L::Q + 29  // pair temporaries take two registers each
                                          : V * L::Q * kW + (kBaseCollision<COLL> == XLBN_KBC ? L::Q * kW + 24 : 24) + (kForcedCollision<COLL> ? 8 * kW : 0) +
                                                (kBaseCollision<COLL> == XLBN_SMAGORINSKY_LES_BGK ? 8 * kW : 0) + 5;
