@@ -38,7 +38,8 @@ def parse():
     p.add_argument("--impl", default="native", choices=["native", "reference"])
     p.add_argument("--n", type=int, default=512, help="edge length per GPU")
     p.add_argument("--lattice", default="D3Q19", choices=list(Q))
-    p.add_argument("--collision", default="BGK", choices=["BGK", "KBC"])
+    p.add_argument("--collision", default="BGK", choices=["BGK", "KBC", "SmagorinskyLESBGK"])
+    p.add_argument("--force", type=float, default=0.0, help="x-component of a constant body force (ForcedCollision / ExactDifference); 0 = none")
     p.add_argument("--policy", default="FP32FP32", choices=list(STORE_BYTES))
     p.add_argument("--config", default="cavity", choices=["cavity", "periodic", "sphere", "tunnel"])
     p.add_argument("--cells-per-thread", type=int, default=0)
@@ -128,7 +129,8 @@ def build_case(args, shape):
         bcs = [EquilibriumBC(rho=1.0, u=(0.02, 0.0, 0.0), indices=lid), FullwayBounceBackBC(indices=walls)]
     elif args.config in ("sphere", "tunnel"):
         bcs = obstacle_bcs(args.config, grid, shape)
-    stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=bcs, collision_type=args.collision, cells_per_thread=args.cells_per_thread)
+    kw = dict(force_vector=np.array([args.force, 0.0, 0.0])) if args.force else {}
+    stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=bcs, collision_type=args.collision, cells_per_thread=args.cells_per_thread, **kw)
     return grid, stepper
 
 

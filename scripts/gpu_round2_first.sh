@@ -1,0 +1,33 @@
+# First GPU call of round 2 (one B200):   gpurun --timeout 2400 -- 'bash scripts/gpu_round2_first.sh'
+# 1. the validated suite, 2. first execution of everything written after round 1's GPU budget was spent,
+# 3. A/B timings that decide round 2's defaults (lean KBC vs default KBC) and first numbers for the extended collision kernels.
+set -x
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 | tee gpurun_out/r2_smoke.log
+timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider --deselect tests/test_zz_first_run_gpu.py 2>&1 | tail -6 | tee gpurun_out/r2_pytest_validated.log
+# -rxX: list xfailed (= a late case FAILED on its first run: read the reason) and xpassed (= it works: promote it)
+timeout 1500 python -m pytest tests/test_zz_first_run_gpu.py -m gpu -q -rxX -p no:cacheprovider 2>&1 | tail -40 | tee gpurun_out/r2_pytest_first_run.log
+: > gpurun_out/r2_matrix.log
+run() { out=$(timeout 400 python bench.py --steps 30 --warmup 3 --no-e2e --no-cpu-baseline "$@" 2>&1 | tail -1); echo "$* => $(echo "$out" | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['clocks'].get('sm_mhz'))" 2>/dev/null || echo "FAILED: $out" | cut -c1-400)" | tee -a gpurun_out/r2_matrix.log; }
+run                                                              # headline, must still read ~41 GLUPS / 0.97
+# KBC: default formulation vs the register-lean one (cells_per_thread 301)
+run --lattice D3Q27 --collision KBC
+run --lattice D3Q27 --collision KBC --cells-per-thread 301
+run --lattice D3Q27 --collision KBC --config periodic
+run --lattice D3Q27 --collision KBC --config periodic --cells-per-thread 301
+run --lattice D3Q27 --collision KBC --config sphere
+run --lattice D3Q27 --collision KBC --config sphere --cells-per-thread 301
+run --lattice D3Q27 --collision KBC --policy FP32FP16
+run --lattice D3Q27 --collision KBC --policy FP32FP16 --cells-per-thread 301
+# extended collision kernels (N4): first numbers
+run --collision SmagorinskyLESBGK
+run --collision SmagorinskyLESBGK --config periodic
+run --config periodic --force 1e-6
+run --collision SmagorinskyLESBGK --config periodic --force 1e-6
+run --lattice D3Q27 --collision SmagorinskyLESBGK --config periodic
+run --lattice D3Q27 --collision KBC --config periodic --force 1e-6
+run --collision SmagorinskyLESBGK --policy FP32FP16
+run --config periodic --force 1e-6 --policy FP64FP64 --n 384
+# one full capture of the lean KBC kernel for the register / stall picture
+ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 4 -c 1 -o gpurun_out/r2_kbc_lean python bench.py --n 256 --lattice D3Q27 --collision KBC --cells-per-thread 301 --steps 3 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/r2_ncu_lean.log 2>&1
+ncu -i gpurun_out/r2_kbc_lean.ncu-rep --page raw --csv > gpurun_out/r2_kbc_lean_raw.csv 2>/dev/null && rm -f gpurun_out/r2_kbc_lean.ncu-rep
