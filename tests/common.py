@@ -41,7 +41,17 @@ WARP_CASES = [
     "warp_periodic_d3q27_kbc",
 ]
 # ... and the collision / forcing options the CUDA path does not have yet: oracle-only for now
-WARP_CASES_N4 = ["warp_periodic_d3q19_bgk_forced", "warp_periodic_d3q19_smagorinsky", "warp_periodic_d3q27_smagorinsky_forced"]
+WARP_CASES_N4 = [  # one per extended instantiation of the fused kernel (csrc/step_inst_ext_*.cu)
+    "warp_periodic_d3q19_bgk_forced",
+    "warp_periodic_d3q19_smagorinsky",
+    "warp_periodic_d3q19_smagorinsky_forced",
+    "warp_periodic_d3q27_bgk_forced",
+    "warp_periodic_d3q27_kbc_forced",
+    "warp_periodic_d3q27_smagorinsky",
+    "warp_periodic_d3q27_smagorinsky_forced",
+    "warp_periodic_d2q9_bgk_forced",
+    "warp_periodic_d2q9_kbc_forced",
+]
 # relative tolerance (max |a-b| / max |b|) per store/compute policy; north-star: 1e-5 fp32, 1e-3 fp16 storage
 RTOL = {"FP32FP32": 1e-5, "FP64FP32": 1e-5, "FP64FP64": 1e-9, "FP32FP16": 1e-3, "FP64FP16": 1e-3}
 

@@ -216,8 +216,9 @@ def periodic(name, lattice, shape, steps, collision, omega, force=None):
     rng = np.random.default_rng(0)
     u0 = (1e-2 * rng.standard_normal((vs.d,) + tuple(shape))).astype(np.float32)
     rho0 = (1.0 + 1e-3 * rng.standard_normal((1,) + tuple(shape))).astype(np.float32)
-    f_init = wp.zeros((vs.q,) + tuple(shape), dtype=wp.float32)
-    f_init = QuadraticEquilibrium()(wp.array(rho0, dtype=wp.float32), wp.array(u0, dtype=wp.float32), f_init)
+    tail = (1,) if vs.d == 2 else ()  # Warp fields of 2-D runs carry a trailing singleton axis (warp_grid.py:26)
+    f_init = wp.zeros((vs.q,) + tuple(shape) + tail, dtype=wp.float32)
+    f_init = QuadraticEquilibrium()(wp.array(rho0.reshape(rho0.shape + tail), dtype=wp.float32), wp.array(u0.reshape(u0.shape + tail), dtype=wp.float32), f_init)
     kw = {} if force is None else dict(force_vector=np.asarray(force, dtype=np.float32))
     stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=[], collision_type=collision, **kw)
     meta = dict(lattice=lattice, collision=collision, shape=np.array(shape), rho0=rho0, u0=u0)
@@ -258,3 +259,15 @@ if __name__ == "__main__":
         periodic("warp_periodic_d3q19_smagorinsky", "D3Q19", (8, 6, 6), 10, "SmagorinskyLESBGK", 1.9)
     if want("warp_periodic_d3q27_smagorinsky_forced"):
         periodic("warp_periodic_d3q27_smagorinsky_forced", "D3Q27", (8, 6, 6), 8, "SmagorinskyLESBGK", 1.95, force=(2e-5, -1e-5, 0.0))
+    if want("warp_periodic_d3q19_smagorinsky_forced"):
+        periodic("warp_periodic_d3q19_smagorinsky_forced", "D3Q19", (6, 8, 4), 8, "SmagorinskyLESBGK", 1.9, force=(0.0, 1e-5, 2e-5))
+    if want("warp_periodic_d3q27_smagorinsky"):
+        periodic("warp_periodic_d3q27_smagorinsky", "D3Q27", (6, 6, 8), 8, "SmagorinskyLESBGK", 1.85)
+    if want("warp_periodic_d3q27_bgk_forced"):
+        periodic("warp_periodic_d3q27_bgk_forced", "D3Q27", (8, 6, 4), 8, "BGK", 1.6, force=(1e-5, 2e-5, -1e-5))
+    if want("warp_periodic_d3q27_kbc_forced"):
+        periodic("warp_periodic_d3q27_kbc_forced", "D3Q27", (6, 8, 6), 8, "KBC", 1.8, force=(-1e-5, 0.0, 2e-5))
+    if want("warp_periodic_d2q9_bgk_forced"):
+        periodic("warp_periodic_d2q9_bgk_forced", "D2Q9", (12, 10), 12, "BGK", 1.5, force=(2e-5, -1e-5))
+    if want("warp_periodic_d2q9_kbc_forced"):
+        periodic("warp_periodic_d2q9_kbc_forced", "D2Q9", (10, 12), 12, "KBC", 1.8, force=(1e-5, 1e-5))
