@@ -164,6 +164,17 @@ int xlbn_mask_indices(int lattice, int mode, const int32_t* indices, long long n
 int xlbn_mask_finalize_jax(int lattice, const int32_t global_dims[3], const int32_t start[3], const int32_t local_dims[3],
                            uint8_t* missing, const uint8_t* solid, void* stream);
 
+/* Replaces MeshBoundaryMasker.warp_implementation (mesh_boundary_masker.py:49-236; 3-D only) for ONE mesh-based BC: surface
+ * voxelisation of a triangle soup.  vertices: device float32 [n_triangles][3 vertices][3], grid units, the whole mesh inside
+ * [0, dims) (the caller checks, as L209-216).  Voxels [i,i+1]^3 that a triangle overlaps become solid (bc_mask = 255); every
+ * other cell with a solid neighbour in direction l gets bc_mask = bc_id and missing[opp[l]] = true.  Other cells are not touched.
+ * edge_test: XLBN_MESH_SCHWARZ_SEIDEL = the published overlap test the reference cites; XLBN_MESH_REFERENCE_LITERAL = the
+ * reference's pre_compute exactly as written (degenerate edge functions; for bit comparison with the reference only).
+ * solid_scratch: device bytes, (nx+2)(ny+2)(nz+2); overwritten. */
+enum xlbn_mesh_edge_test { XLBN_MESH_SCHWARZ_SEIDEL = 0, XLBN_MESH_REFERENCE_LITERAL = 1 };
+int xlbn_mask_mesh(int lattice, const float* vertices, long long n_triangles, int bc_id, int edge_test, const int32_t dims[3],
+                   uint8_t* bc_mask, uint8_t* missing /* bool [q][nx][ny][nz] */, uint8_t* solid_scratch, void* stream);
+
 /* bool [q][n_cells] -> uint32 [n_cells] bitmask consumed by xlbn_step. */
 int xlbn_pack_missing(int q, const uint8_t* missing, uint32_t* bits, long long n_cells, void* stream);
 

@@ -595,6 +595,95 @@ def momentum_transfer(bc: BC, f_post_collision, bc_mask, missing, lat: Lattice, 
 
 
 # --------------------------------------------------------------------------------------------
+# Mesh-based masks  (boundary_masker/mesh_boundary_masker.py:49-236)
+# --------------------------------------------------------------------------------------------
+
+
+def _tri_setup(v0, v1, v2, edge_test):
+    """pre_compute (mesh_boundary_masker.py:65-99) in float32, one rounding per operation in the reference's order.
+    edge_test="reference": the edge normals / offsets exactly as written there (both components from e[ax0], v[ax0]);
+    edge_test="schwarz_seidel": the published form the reference cites (n_e = sgn (-e[ax1], e[ax0]), offset from v[ax0], v[ax1])."""
+    f = np.float32
+    v = [np.asarray(x, dtype=f) for x in (v0, v1, v2)]
+    n = np.cross(v[1] - v[0], v[2] - v[0]).astype(f)
+    length = np.sqrt((n * n).sum(dtype=f))
+    valid = bool(length > 0)
+    n = (n / length).astype(f) if valid else np.zeros(3, f)
+    corner = (n > 0).astype(f)
+    dist1 = (n * (corner - v[0])).sum(dtype=f)
+    dist2 = (n * ((f(1.0) - corner) - v[0])).sum(dtype=f)
+    e = [v[(i + 1) % 3] - v[i] for i in range(3)]
+    ne0, ne1, de = np.zeros((3, 3), f), np.zeros((3, 3), f), np.zeros((3, 3), f)
+    for ax0 in range(3):
+        ax1, ax2 = (ax0 + 1) % 3, (ax0 + 2) % 3
+        sgn = f(-1.0) if n[ax2] < 0 else f(1.0)
+        for i in range(3):
+            a, b = (ax0, ax0) if edge_test == "reference" else (ax1, ax1)
+            ne0[i, ax0] = f(-1.0) * sgn * e[i][a]
+            ne1[i, ax0] = sgn * e[i][ax0]
+            vb = v[i][ax0] if edge_test == "reference" else v[i][b]
+            de[i, ax0] = (f(-1.0) * (ne0[i, ax0] * v[i][ax0] + ne1[i, ax0] * vb) + max(f(0.0), ne0[i, ax0])) + max(f(0.0), ne1[i, ax0])
+    lo = np.minimum(np.minimum(v[0], v[1]), v[2])
+    hi = np.maximum(np.maximum(v[0], v[1]), v[2])
+    return dict(n=n, dist1=dist1, dist2=dist2, ne0=ne0, ne1=ne1, de=de, lo=lo, hi=hi, valid=valid)
+
+
+def _tri_box_overlap(t, low):
+    """triangle_box_intersect (L110-128) for unit boxes at `low` [..., 3] (float32), after the inclusive bounding-box
+    overlap that wp.mesh_query_aabb applies (L136)."""
+    f = np.float32
+    low = np.asarray(low, dtype=f)
+    hit = np.all((t["lo"] <= low + f(1.0)) & (t["hi"] >= low), axis=-1)
+    if not t["valid"]:
+        return np.zeros_like(hit)
+    n = t["n"]
+    nl = (n[0] * low[..., 0] + n[1] * low[..., 1]) + n[2] * low[..., 2]
+    hit &= (nl + t["dist1"]) * (nl + t["dist2"]) <= 0
+    for ax0 in range(3):
+        ax1 = (ax0 + 1) % 3
+        for i in range(3):
+            hit &= (t["ne0"][i, ax0] * low[..., ax0] + t["ne1"][i, ax0] * low[..., ax1]) + t["de"][i, ax0] >= 0
+    return hit
+
+
+def mesh_solid_voxels(vertices, shape, edge_test="schwarz_seidel"):
+    """bool [nx+2, ny+2, nz+2]: voxel (i, j, k) -> [i+1, j+1, k+1] is True iff some triangle overlaps the box [i, i+1]^3
+    (mesh_voxel_intersect, L133-148).  vertices: (3 T, 3), three consecutive rows per triangle (L219-223)."""
+    tri = np.asarray(vertices, dtype=np.float32).reshape(-1, 3, 3)
+    solid = np.zeros(tuple(s + 2 for s in shape), dtype=bool)
+    for v0, v1, v2 in tri:
+        t = _tri_setup(v0, v1, v2, edge_test)
+        lo = np.maximum(-1, np.ceil(t["lo"] - np.float32(1.0)).astype(np.int64))
+        hi = np.minimum(np.array(shape), np.floor(t["hi"]).astype(np.int64))
+        if np.any(lo > hi):
+            continue
+        ax = [np.arange(lo[k], hi[k] + 1) for k in range(3)]
+        I, J, K = np.meshgrid(*ax, indexing="ij")
+        hit = _tri_box_overlap(t, np.stack([I, J, K], axis=-1).astype(np.float32))
+        solid[I[hit] + 1, J[hit] + 1, K[hit] + 1] = True
+    return solid
+
+
+def build_masks_mesh(vertices, bc_id, bc_mask, missing, lat: Lattice, edge_test="schwarz_seidel"):
+    """MeshBoundaryMasker kernel (L153-190) applied on top of existing masks: solid voxels -> 255; every other cell with a
+    solid neighbour in direction l -> bc_mask = id, missing[opp[l]] = True."""
+    if lat.d != 3:
+        raise NotImplementedError("This Operator is not implemented in 2D!")  # L27-28
+    shape = bc_mask.shape[1:]
+    solid = mesh_solid_voxels(vertices, shape, edge_test)
+    inner = solid[1:-1, 1:-1, 1:-1]
+    bc_mask, missing = bc_mask.copy(), missing.copy()
+    bc_mask[0][inner] = 255
+    for l in range(1, lat.q):
+        c = lat.c[:, l]
+        nb = solid[1 + c[0] : 1 + c[0] + shape[0], 1 + c[1] : 1 + c[1] + shape[1], 1 + c[2] : 1 + c[2] + shape[2]]
+        sel = nb & ~inner
+        bc_mask[0][sel] = bc_id
+        missing[lat.opp[l]][sel] = True
+    return bc_mask, missing
+
+
+# --------------------------------------------------------------------------------------------
 # x-slab halo exchange emulation  (distribute/distribute.py:23-44)
 # --------------------------------------------------------------------------------------------
 

@@ -229,6 +229,39 @@ def periodic(name, lattice, shape, steps, collision, omega, force=None):
     run_and_save(name, meta, stepper, [], steps, omega, vs.d, f_init=np.asarray(f_init))
 
 
+def mesh_shapes():
+    """Small closed triangle soups at generic (non-lattice-aligned) positions: a tetrahedron, a rotated box, an octahedron."""
+    tet = np.array([[2.21, 1.37, 1.11], [9.63, 3.19, 2.87], [5.02, 9.43, 3.33], [5.57, 4.21, 8.79]])
+    tet_f = [(0, 1, 2), (0, 3, 1), (1, 3, 2), (2, 3, 0)]
+    a, b = 0.37, 0.21  # rotated box
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]) @ np.array([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]])
+    corners = np.array([[x, y, z] for x in (-2.6, 2.6) for y in (-1.9, 1.9) for z in (-1.4, 1.4)]) @ R.T + np.array([6.13, 5.41, 4.87])
+    box_f = [(0, 1, 3), (0, 3, 2), (4, 6, 7), (4, 7, 5), (0, 4, 5), (0, 5, 1), (2, 3, 7), (2, 7, 6), (0, 2, 6), (0, 6, 4), (1, 5, 7), (1, 7, 3)]
+    octa = np.array([[3.3, 0, 0], [-3.3, 0, 0], [0, 2.9, 0], [0, -2.9, 0], [0, 0, 2.7], [0, 0, -2.7]]) + np.array([6.07, 5.53, 4.61])
+    octa_f = [(0, 2, 4), (2, 1, 4), (1, 3, 4), (3, 0, 4), (2, 0, 5), (1, 2, 5), (3, 1, 5), (0, 3, 5)]
+    return {"tetrahedron": (tet, tet_f), "box": (corners, box_f), "octahedron": (octa, octa_f)}
+
+
+def mesh_masks(name, lattice, shape, body):
+    """MeshBoundaryMasker.warp_implementation (mesh_boundary_masker.py:193-236) on zeroed masks, through the reference's own
+    kernel (triangle / voxel test L60-148) with wp.Mesh / wp.mesh_query_aabb served by the stand-in's brute-force mesh."""
+    from xlb.operator.boundary_masker import MeshBoundaryMasker
+
+    vs, pp = init(lattice)
+    grid = grid_factory(shape)
+    P, faces = mesh_shapes()[body]
+    verts = np.array([P[i] for f in faces for i in f], dtype=np.float64)
+    bc = HalfwayBounceBackBC(mesh_vertices=verts.copy())
+    bc_mask = grid.create_field(cardinality=1, dtype=xlb.Precision.UINT8)
+    missing = grid.create_field(cardinality=vs.q, dtype=xlb.Precision.BOOL)
+    t0 = time.time()
+    bc_mask, missing = MeshBoundaryMasker(vs, pp, BE)(bc, bc_mask, missing)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, lattice=lattice, shape=np.array(shape), vertices=verts, bc_id=np.int64(bc.id), bc_mask=np.asarray(bc_mask),
+                        missing_bits=pack_bits(missing), backend="WARP")  # fmt: skip
+    print(f"{name}: {int((np.asarray(bc_mask) == 255).sum())} solid, {int((np.asarray(bc_mask) == bc.id).sum())} boundary cells in {time.time() - t0:.0f} s", flush=True)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
 
@@ -269,5 +302,10 @@ if __name__ == "__main__":
         periodic("warp_periodic_d3q27_kbc_forced", "D3Q27", (6, 8, 6), 8, "KBC", 1.8, force=(-1e-5, 0.0, 2e-5))
     if want("warp_periodic_d2q9_bgk_forced"):
         periodic("warp_periodic_d2q9_bgk_forced", "D2Q9", (12, 10), 12, "BGK", 1.5, force=(2e-5, -1e-5))
+    for body in ("tetrahedron", "box", "octahedron"):
+        for lattice in ("D3Q19", "D3Q27"):
+            n = f"warp_mesh_{body}_{lattice.lower()}"
+            if want(n):
+                mesh_masks(n, lattice, (12, 11, 10), body)
     if want("warp_periodic_d2q9_kbc_forced"):
         periodic("warp_periodic_d2q9_kbc_forced", "D2Q9", (10, 12), 12, "KBC", 1.8, force=(1e-5, 1e-5))

@@ -55,9 +55,10 @@ def mirror():
     return lib
 
 
-def mirror_run(lib, g, steps=None, v=1, lean_kbc=False):
-    """The user loop (step, swap) through the host-compiled kernel source; masks and aux data from the oracle helpers."""
-    lat, bcs, bc_mask, missing = oracle_masks(g, "warp")
+def mirror_run(lib, g, steps=None, v=1, lean_kbc=False, masks=None):
+    """The user loop (step, swap) through the host-compiled kernel source; masks and aux data from the oracle helpers
+    (or `masks` = (lat, bcs, bc_mask, missing) built by the caller)."""
+    lat, bcs, bc_mask, missing = masks if masks is not None else oracle_masks(g, "warp")
     cdt, sdt = O.policy_dtypes(g["policy"])
     fa = np.ascontiguousarray(g["f_init"], dtype=sdt).copy()
     fb = fa.copy()
@@ -148,6 +149,29 @@ def test_lean_kbc_variant_matches_the_reference_vectors(mirror, name):
     lean = mirror_run(mirror, g, lean_kbc=True)
     assert rel_err(lean, g["f_final"]) <= RTOL[g["policy"]]
     assert rel_err(lean, mirror_run(mirror, g)) <= 3e-6
+
+
+def test_wind_tunnel_with_a_voxelised_mesh_body(mirror):
+    """examples/cfd/windtunnel_3d.py:66-96 in small: Fullway walls, Regularized inlet, outflow, and a Halfway body given as a
+    triangle mesh (masks from the mesh voxeliser: a 255 shell with boundary cells around it) — kernel source vs the C oracle."""
+    from test_mesh_masker import load_mesh_case
+
+    shape, lat = (24, 11, 10), O.Lattice("D3Q27")
+    box, bne = O.bounding_box_indices(shape), O.bounding_box_indices(shape, remove_edges=True)
+    walls = np.unique(np.concatenate([box[k] for k in ("bottom", "top", "front", "back")], axis=1), axis=-1)
+    bcs = [O.BC("fullway", 1, walls), O.BC("regularized", 2, bne["left"], bc_type="velocity", prescribed=np.array([0.03, 0.0, 0.0])),
+           O.BC("outflow", 3, bne["right"]), O.BC("halfway", 4, np.zeros((3, 0), np.int64))]  # fmt: skip
+    bc_mask, missing = O.build_masks(bcs[:3], shape, lat, flavor="warp")
+    verts = load_mesh_case("warp_mesh_octahedron_d3q27")["vertices"] + np.array([2.0, 0.0, 0.0])
+    bc_mask, missing = O.build_masks_mesh(verts, 4, bc_mask, missing, lat)
+    assert (bc_mask == 255).sum() > 50 and (bc_mask == 4).sum() > 100
+    g = dict(lattice="D3Q27", policy="FP32FP32", collision="KBC", shape=shape, omega=1.6, steps=20, f_init=O.initialize_eq(shape, lat),
+             force_vector=None, smagorinsky=0.17)  # fmt: skip
+    f = mirror_run(mirror, g, masks=(lat, bcs, bc_mask, missing))
+    ref = lbm_c.run(g["f_init"], bc_mask, missing, bcs, 1.6, lat, 20, "FP32FP32", "KBC")
+    assert np.isfinite(f).all() and rel_err(f, ref) <= 1e-5
+    solid = bc_mask[0] == 255
+    assert np.array_equal(f[:, solid], g["f_init"][:, solid])  # nse_stepper.py:356-358: solid cells are never written
 
 
 def test_bc_kind_codes_agree_with_the_header():

@@ -69,7 +69,7 @@ def test_warp_and_jax_standins_are_installed_only_when_missing():
     assert np.allclose(jnp.maximum(0.0, np.array([-1.0, 2.0])), [0.0, 2.0])
 
 
-@pytest.mark.parametrize("script", ["examples/cavity_mlups.py", "examples/sphere_kbc.py", "examples/cavity_2d.py", "bench.py", "__graft_entry__.py", "scripts/mgpu_check.py"])
+@pytest.mark.parametrize("script", ["examples/cavity_mlups.py", "examples/sphere_kbc.py", "examples/cavity_2d.py", "examples/windtunnel_mesh.py", "bench.py", "__graft_entry__.py", "scripts/mgpu_check.py"])
 def test_scripts_compile(script):
     py_compile.compile(os.path.join(ROOT, script), doraise=True)
 
@@ -117,3 +117,23 @@ def test_stepper_collision_options_mirror_the_reference_ctor():
     xlb.init(velocity_set=xlb.velocity_set.D2Q9(pp, ComputeBackend.WARP), default_backend=ComputeBackend.WARP, default_precision_policy=pp)
     with pytest.raises(NotImplementedError):  # the reference functional reads c[2, l]: 3-D only
         SmagorinskyLESBGK()
+
+
+def test_read_stl_binary_and_ascii(tmp_path):
+    from xlb_b200.utils import read_stl
+
+    tris = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]], [[0, 0, 1], [1, 0.5, 1], [0.25, 1, 1]]], dtype=np.float32)
+    rec = np.zeros(2, dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]))
+    rec["v"] = tris
+    binary = tmp_path / "b.stl"
+    binary.write_bytes(b"binary stl".ljust(80, b" ") + np.uint32(2).tobytes() + rec.tobytes())
+    ascii_ = tmp_path / "a.stl"
+    body = "".join("facet normal 0 0 1\n outer loop\n" + "".join(f"  vertex {x} {y} {z}\n" for x, y, z in t) + " endloop\nendfacet\n" for t in tris)
+    ascii_.write_text("solid s\n" + body + "endsolid s\n")
+    for path in (binary, ascii_):
+        v = read_stl(str(path))
+        assert v.shape == (6, 3) and v.dtype == np.float64 and np.allclose(v, tris.reshape(-1, 3))
+    bad = tmp_path / "c.stl"
+    bad.write_text("hello")
+    with pytest.raises(ValueError):
+        read_stl(str(bad))

@@ -130,3 +130,78 @@ def test_first_run_of_the_extended_collision_operators():
     assert proc.returncode == 0, proc.stderr[-1500:]
     worst = [float(l.split()[1]) for l in proc.stdout.splitlines() if l.startswith("RESULT")][0]
     assert worst <= 2e-6, worst
+
+
+MESH_CHILD = r"""
+import sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+import numpy as np, torch
+import xlb_b200 as xlb
+from xlb_b200.compute_backend import ComputeBackend
+from xlb_b200.grid import grid_factory
+from xlb_b200.operator.boundary_condition import ExtrapolationOutflowBC, FullwayBounceBackBC, HalfwayBounceBackBC, RegularizedBC
+from xlb_b200.operator.boundary_masker import MeshBoundaryMasker
+from xlb_b200.operator.stepper import IncompressibleNavierStokesStepper
+from oracle import lbm_c
+from oracle import lbm_numpy as O
+from common import rel_err, unpack_bits
+from test_mesh_masker import MESH_CASES, load_mesh_case
+pp, be = xlb.PrecisionPolicy.FP32FP32, ComputeBackend.WARP
+ok = True
+for name in MESH_CASES:
+    g = load_mesh_case(name)
+    lattice, shape = str(g["lattice"]), tuple(int(s) for s in g["shape"])
+    vs = getattr(xlb.velocity_set, lattice)(pp, be)
+    xlb.init(velocity_set=vs, default_backend=be, default_precision_policy=pp)
+    grid = grid_factory(shape)
+    lat = O.Lattice(lattice)
+    for mode in ("reference", "schwarz_seidel"):
+        bc = HalfwayBounceBackBC(mesh_vertices=g["vertices"].copy())
+        bc.id = int(g["bc_id"])
+        bc_mask = grid.create_field(cardinality=1, dtype=xlb.Precision.UINT8)
+        missing = grid.create_field(cardinality=vs.q, dtype=xlb.Precision.BOOL)
+        bc_mask, missing = MeshBoundaryMasker(vs, pp, be, edge_test=mode)(bc, bc_mask, missing)
+        bm, mm = O.build_masks_mesh(g["vertices"], bc.id, np.zeros((1,) + shape, np.uint8), np.zeros((lat.q,) + shape, bool), lat, edge_test=mode)
+        same = np.array_equal(bc_mask.numpy(), bm) and np.array_equal(missing.numpy(), mm)
+        if mode == "reference":
+            same = same and np.array_equal(bc_mask.numpy(), g["bc_mask"]) and np.array_equal(missing.numpy(), unpack_bits(g["missing_bits"], lat.q))
+        ok = ok and same
+        print("MASK", name, mode, same)
+# a wind-tunnel style run with a mesh body (examples/cfd/windtunnel_3d.py:66-96), against the C oracle on the same masks
+g = load_mesh_case("warp_mesh_octahedron_d3q27")
+shape = (24, 11, 10)
+vs = xlb.velocity_set.D3Q27(pp, be)
+xlb.init(velocity_set=vs, default_backend=be, default_precision_policy=pp)
+grid = grid_factory(shape)
+box, bne = grid.bounding_box_indices(), grid.bounding_box_indices(remove_edges=True)
+walls = [box["bottom"][i] + box["top"][i] + box["front"][i] + box["back"][i] for i in range(3)]
+walls = np.unique(np.array(walls), axis=-1).tolist()
+bcs = [FullwayBounceBackBC(indices=walls), RegularizedBC("velocity", prescribed_value=(0.03, 0.0, 0.0), indices=bne["left"]),
+       ExtrapolationOutflowBC(indices=bne["right"]), HalfwayBounceBackBC(mesh_vertices=g["vertices"] + np.array([2.0, 0.0, 0.0]))]
+stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=bcs, collision_type="KBC")
+f_0, f_1, bc_mask, missing = stepper.prepare_fields()
+lat = O.Lattice("D3Q27")
+obcs = [O.BC("fullway", bcs[0].id, np.array(walls)), O.BC("regularized", bcs[1].id, np.array(bne["left"]), bc_type="velocity", prescribed=np.array([0.03, 0.0, 0.0])),
+        O.BC("outflow", bcs[2].id, np.array(bne["right"])), O.BC("halfway", bcs[3].id, np.zeros((3, 0), np.int64))]
+bm, mm = O.build_masks(obcs[:3], shape, lat, flavor="warp")
+bm, mm = O.build_masks_mesh(g["vertices"] + np.array([2.0, 0.0, 0.0]), bcs[3].id, bm, mm, lat)
+same = np.array_equal(bc_mask.numpy(), bm) and np.array_equal(missing.numpy(), mm)
+print("MASK windtunnel", same)
+for i in range(20):
+    f_0, f_1 = stepper(f_0, f_1, bc_mask, missing, 1.6, i)
+    f_0, f_1 = f_1, f_0
+ref = lbm_c.run(O.initialize_eq(shape, lat), bm, mm, obcs, 1.6, lat, 20, "FP32FP32", "KBC")
+err = rel_err(f_0.numpy(), ref)
+print("RESULT", ok and same, err)
+"""
+
+
+@LATE
+def test_first_run_of_the_mesh_boundary_masker():
+    """xlbn_mask_mesh through MeshBoundaryMasker: both edge tests vs the oracle (the literal one also vs the reference's masks),
+    and a wind-tunnel run with a mesh body vs the C oracle on the same masks."""
+    proc = subprocess.run([sys.executable, "-c", MESH_CHILD % {"root": ROOT}], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert proc.returncode == 0, proc.stderr[-1500:]
+    res = [l.split() for l in proc.stdout.splitlines() if l.startswith("RESULT")][0]
+    assert res[1] == "True", proc.stdout[-1500:]
+    assert float(res[2]) <= 1e-5

@@ -23,7 +23,7 @@ from xlb_b200.default_config import DefaultConfig
 from xlb_b200.helper.check_boundary_overlaps import check_bc_overlaps
 from xlb_b200.helper.nse_solver import create_nse_fields
 from xlb_b200.operator.boundary_condition.boundary_condition import ImplementationStep
-from xlb_b200.operator.boundary_masker import IndicesBoundaryMasker
+from xlb_b200.operator.boundary_masker import IndicesBoundaryMasker, MeshBoundaryMasker
 from xlb_b200.operator.collision import BGK, KBC, ForcedCollision, SmagorinskyLESBGK
 from xlb_b200.operator.equilibrium import QuadraticEquilibrium
 from xlb_b200.operator.macroscopic import Macroscopic
@@ -98,8 +98,9 @@ class IncompressibleNavierStokesStepper(Stepper):
     @classmethod
     def _process_boundary_conditions(cls, boundary_conditions, bc_mask, missing_mask, grid=None):
         check_bc_overlaps(boundary_conditions, DefaultConfig.velocity_set.d, DefaultConfig.default_backend)
-        if any(bc.mesh_vertices is not None for bc in boundary_conditions):
-            raise NotImplementedError("mesh-based boundary conditions (MeshBoundaryMasker) are outside the scope of this backend")
+        bc_with_vertices = [bc for bc in boundary_conditions if bc.mesh_vertices is not None]
+        if bc_with_vertices and grid is not None and grid.nDevices > 1:
+            raise NotImplementedError("mesh-based boundary conditions on an x-slab grid: voxelise on one device and pass indices instead")
         masker = IndicesBoundaryMasker(
             velocity_set=DefaultConfig.velocity_set,
             precision_policy=DefaultConfig.default_precision_policy,
@@ -111,6 +112,14 @@ class IncompressibleNavierStokesStepper(Stepper):
             if grid is not None and grid.nDevices > 1:
                 kw = dict(start_index=grid.start_index, global_shape=grid.shape)
             bc_mask, missing_mask = masker(bc_with_indices, bc_mask, missing_mask, **kw)
+        if DefaultConfig.velocity_set.d == 3 and bc_with_vertices:  # nse_stepper.py:119-127
+            mesh_masker = MeshBoundaryMasker(
+                velocity_set=DefaultConfig.velocity_set,
+                precision_policy=DefaultConfig.default_precision_policy,
+                compute_backend=DefaultConfig.default_backend,
+            )
+            for bc in bc_with_vertices:
+                bc_mask, missing_mask = mesh_masker(bc, bc_mask, missing_mask)
         return bc_mask, missing_mask
 
     @staticmethod

@@ -40,3 +40,21 @@ def save_fields_vtk(fields, timestep, output_dir=".", prefix="fields", **kwargs)
             fh.write(f"SCALARS {key} float 1\nLOOKUP_TABLE default\n")
             np.savetxt(fh, np.asarray(arr, dtype=np.float32).reshape(dims).transpose(2, 1, 0).reshape(-1), fmt="%.7g")
     return name
+
+
+def read_stl(path):
+    """Triangle soup of an STL file (binary or ASCII) as a float64 array (3 T, 3): three consecutive rows per triangle —
+    the layout `mesh_vertices` of a mesh-based boundary condition expects (reference scripts obtain it from
+    `trimesh.load_mesh(path, process=False).vertices`, examples/cfd/windtunnel_3d.py:76-78)."""
+    with open(path, "rb") as fh:
+        data = fh.read()
+    if len(data) >= 84:
+        n = int(np.frombuffer(data, dtype="<u4", count=1, offset=80)[0])
+        if len(data) == 84 + 50 * n:  # binary: 80-byte header, count, 50-byte records (normal, 3 vertices, attribute)
+            rec = np.frombuffer(data, dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]), count=n, offset=84)
+            return rec["v"].reshape(-1, 3).astype(np.float64)
+    rows = [line.split()[1:4] for line in data.decode("ascii", "replace").splitlines() if line.strip().startswith("vertex")]
+    verts = np.array(rows, dtype=np.float64).reshape(-1, 3)
+    if verts.shape[0] == 0 or verts.shape[0] % 3:
+        raise ValueError(f"{path}: not an STL file (found {verts.shape[0]} vertices)")
+    return verts
