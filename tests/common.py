@@ -27,6 +27,11 @@ STEP_CASES = [
 # gamma = <dh|ds>/(eps + <dh|dh>) becomes 0/0-like and the run is ill-conditioned — the numpy oracle in fp32 and in fp64
 # differ by 2e-3 after 60 steps — so it cannot pin anything.)
 EXTRA_CASES_2D = ["channel2d_d2q9_bgk_outflow_fp32", "channel2d_d2q9_bgk_zouhe_pressure_fp32"]
+# ... and the non-trivial BCs under the other precision policies.  Under FP32FP16 the JAX path keeps the prescribed inlet velocity in
+# the BC object (compute dtype) while the Warp path — and this library — keeps it in f_1[0, cell] in the STORE dtype, i.e. rounded
+# to fp16: the Warp-convention results sit 7e-4 from this JAX vector, inside the 1e-3 fp16 tolerance.
+EXTRA_CASES_POLICIES = ["sphere_d3q19_bgk_fp32fp16", "sphere_d3q27_kbc_fp64fp32", "sphere_d3q27_kbc_zouhe_pressure_fp64"]
+LATE_CASES = EXTRA_CASES_2D + EXTRA_CASES_POLICIES
 # Produced by the reference's WARP backend itself, executed per cell under oracle/refshim's interpretive `warp`
 # (tests/golden/make_golden_warp.py).  All FP32FP32.
 WARP_CASES = [

@@ -273,6 +273,9 @@ if __name__ == "__main__":
     sphere("sphere_d3q19_bgk_donothing_fp32", "D3Q19", "FP32FP32", (32, 14, 14), 30, "BGK", omega=1.2, outlet="donothing")
     periodic("periodic_d3q19_bgk_fp32", "D3Q19", "FP32FP32", (12, 10, 8), 30, "BGK", 1.5)
     periodic("periodic_d3q27_kbc_fp32", "D3Q27", "FP32FP32", (12, 10, 8), 30, "KBC", 1.8)
+    sphere("sphere_d3q19_bgk_fp32fp16", "D3Q19", "FP32FP16", (32, 14, 14), 30, "BGK", omega=1.5)
+    sphere("sphere_d3q27_kbc_fp64fp32", "D3Q27", "FP64FP32", (32, 14, 14), 30, "KBC", omega=1.6)
+    sphere("sphere_d3q27_kbc_zouhe_pressure_fp64", "D3Q27", "FP64FP64", (28, 12, 12), 25, "KBC", omega=1.7, outlet="pressure", inlet="zouhe")
     channel2d("channel2d_d2q9_bgk_outflow_fp32", "FP32FP32", (60, 24), 60, "BGK", 1.6)
     channel2d("channel2d_d2q9_bgk_zouhe_pressure_fp32", "FP32FP32", (60, 24), 60, "BGK", 1.5, outlet="pressure", inlet="zouhe")
     # body force (ForcedCollision + ExactDifference, as examples/cfd/turbulent_channel_3d.py drives its channel): target for round 2

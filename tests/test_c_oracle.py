@@ -4,14 +4,14 @@ produced by the reference's own Python and against the numpy oracle.  CPU only."
 import numpy as np
 import pytest
 
-from common import EXTRA_CASES_2D, STEP_CASES, load_golden, oracle_bcs, oracle_run, rel_err
+from common import LATE_CASES, STEP_CASES, load_golden, oracle_bcs, oracle_run, rel_err
 from oracle import lbm_c
 from oracle import lbm_numpy as O
 
 pytestmark = pytest.mark.skipif(not lbm_c.available(), reason="oracle/liblbm_ref.so not built (make -C oracle)")
 
 
-@pytest.mark.parametrize("name", STEP_CASES + EXTRA_CASES_2D)
+@pytest.mark.parametrize("name", STEP_CASES + LATE_CASES)
 def test_c_oracle_matches_reference_vectors(name):
     g = load_golden(name)
     lat = O.Lattice(g["lattice"])

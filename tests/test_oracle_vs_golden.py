@@ -4,11 +4,11 @@
 import numpy as np
 import pytest
 
-from common import EXTRA_CASES_2D, STEP_CASES, load_golden, oracle_run, rel_err, unpack_bits
+from common import LATE_CASES, STEP_CASES, load_golden, oracle_run, rel_err, unpack_bits
 from oracle import lbm_numpy as O
 
 
-@pytest.mark.parametrize("name", STEP_CASES + EXTRA_CASES_2D)
+@pytest.mark.parametrize("name", STEP_CASES + LATE_CASES)
 def test_step_cases(name):
     g = load_golden(name)
     lat = O.Lattice(g["lattice"])

@@ -14,7 +14,7 @@ import sys
 
 import pytest
 
-from common import EXTRA_CASES_2D, STEP_CASES, WARP_CASES, WARP_CASES_N4
+from common import LATE_CASES, STEP_CASES, WARP_CASES, WARP_CASES_N4
 
 pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU execution of code / cases added after the round-1 GPU budget was spent")]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -188,7 +188,7 @@ def step_group(cases):
     return STEP_GROUP % {"root": ROOT, "cases": cases}
 
 
-LATE_2D = [(n, b, 0) for n in EXTRA_CASES_2D for b in ("WARP", "JAX")]
+LATE_2D = [(n, b, 0) for n in LATE_CASES for b in ("WARP", "JAX")]
 WARP_VECTORS = [(n, "WARP", 0) for n in WARP_CASES]
 N4_VECTORS = [(n, "WARP", 0) for n in WARP_CASES_N4]
 LEAN_KBC = [(n, "WARP", 301) for n in KBC_CASES]
