@@ -80,6 +80,19 @@ def test_device_triangle_code_on_the_host_equals_the_oracle(mirror, edge_test):
     assert O.mesh_solid_voxels(soups[0], shape, "schwarz_seidel").sum() > 5 * O.mesh_solid_voxels(soups[0], shape, "reference").sum()
 
 
+def test_slab_voxelisation_equals_the_slice_of_the_global_one(mirror):
+    """x-slabs: every rank voxelises the mesh shifted into its local coordinates, with one cell of halo — the device code's
+    result for a slab must be the corresponding slice of the global (padded) solid volume."""
+    shape = (12, 11, 10)
+    verts = load_mesh_case("warp_mesh_box_d3q27")["vertices"]
+    whole = O.mesh_solid_voxels(verts, shape)
+    for n_slabs in (2, 3, 4):
+        h = shape[0] // n_slabs
+        for r in range(n_slabs):
+            local = mirror_solid(mirror, verts - np.array([r * h, 0.0, 0.0]), (h,) + shape[1:], 0)
+            assert np.array_equal(local, whole[r * h : (r + 1) * h + 2])
+
+
 # ---- independent check of the published test: separating axes (Akenine-Moeller), float64 ---------------------------------
 
 

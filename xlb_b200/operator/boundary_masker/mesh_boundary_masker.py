@@ -16,6 +16,9 @@ three consecutive rows per triangle).  The reference finds triangle / voxel pair
   masks bit for bit (tests/golden/warp_mesh_*.npz) and exists for that comparison; it does not voxelise a body.
 
 Call: ``masker(bc, bc_mask, missing_mask) -> (bc_mask, missing_mask)`` for ONE mesh-based BC (reference L193-198).
+Slab decomposition: ``start_index`` (global coordinate of local cell 0) and ``global_shape`` as extra keywords; the mesh is
+given in GLOBAL grid units, every rank voxelises the triangles that reach its slab (plus one cell of halo, so that boundary
+cells next to a solid voxel of the neighbouring slab are found).
 """
 
 import numpy as np
@@ -37,7 +40,7 @@ class MeshBoundaryMasker(Operator):
             raise ValueError(f"edge_test must be one of {sorted(EDGE_TESTS)}, got {edge_test!r}")
         self.edge_test = edge_test
 
-    def _run(self, bc, bc_mask, missing_mask):
+    def _run(self, bc, bc_mask, missing_mask, start_index=None, global_shape=None):
         vs = self.velocity_set
         assert bc.mesh_vertices is not None, f'Please provide the mesh vertices for {bc.__class__.__name__} BC using keyword "mesh_vertices"!'
         assert bc.indices is None, f"Please use IndicesBoundaryMasker operator if {bc.__class__.__name__} is imposed on known indices of the grid!"
@@ -52,11 +55,14 @@ class MeshBoundaryMasker(Operator):
         dims = native.dims_of(missing_mask, vs.d)
         if missing_mask.shape[0] != vs.q or bc_mask.shape[0] != 1 or native.dims_of(bc_mask, vs.d) != dims:
             raise ValueError("bc_mask / missing_mask shapes do not match the velocity set")
+        domain = tuple(global_shape) if global_shape is not None else tuple(dims)
         mesh_min, mesh_max = mesh_vertices.min(axis=0), mesh_vertices.max(axis=0)
-        if any(mesh_min < 0) or any(mesh_max >= np.array(dims)):
+        if any(mesh_min < 0) or any(mesh_max >= np.array(domain)):
             raise ValueError(
-                f"Mesh extents ({mesh_min}, {mesh_max}) exceed domain dimensions {tuple(dims)}. The mesh must be fully contained within the domain."
+                f"Mesh extents ({mesh_min}, {mesh_max}) exceed domain dimensions {domain}. The mesh must be fully contained within the domain."
             )
+        if start_index is not None:  # local coordinates of this slab; triangles elsewhere fall outside the padded volume and are skipped
+            mesh_vertices = mesh_vertices - np.asarray(start_index, dtype=mesh_vertices.dtype)[: vs.d]
         assert not getattr(bc, "needs_mesh_distance", False), 'Please use "MeshDistanceBoundaryMasker" if this BC needs mesh distance!'
         bc.__dict__.pop("mesh_vertices", None)  # reference L212-213: the BC is done with its vertices
 
@@ -71,9 +77,9 @@ class MeshBoundaryMasker(Operator):
         return bc_mask, missing_mask
 
     @Operator.register_backend(ComputeBackend.JAX)
-    def jax_implementation(self, bc, bc_mask, missing_mask):
-        return self._run(bc, bc_mask, missing_mask)
+    def jax_implementation(self, bc, bc_mask, missing_mask, start_index=None, global_shape=None):
+        return self._run(bc, bc_mask, missing_mask, start_index, global_shape)
 
     @Operator.register_backend(ComputeBackend.WARP)
-    def warp_implementation(self, bc, bc_mask, missing_mask):
-        return self._run(bc, bc_mask, missing_mask)
+    def warp_implementation(self, bc, bc_mask, missing_mask, start_index=None, global_shape=None):
+        return self._run(bc, bc_mask, missing_mask, start_index, global_shape)

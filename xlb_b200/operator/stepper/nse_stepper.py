@@ -99,8 +99,6 @@ class IncompressibleNavierStokesStepper(Stepper):
     def _process_boundary_conditions(cls, boundary_conditions, bc_mask, missing_mask, grid=None):
         check_bc_overlaps(boundary_conditions, DefaultConfig.velocity_set.d, DefaultConfig.default_backend)
         bc_with_vertices = [bc for bc in boundary_conditions if bc.mesh_vertices is not None]
-        if bc_with_vertices and grid is not None and grid.nDevices > 1:
-            raise NotImplementedError("mesh-based boundary conditions on an x-slab grid: voxelise on one device and pass indices instead")
         masker = IndicesBoundaryMasker(
             velocity_set=DefaultConfig.velocity_set,
             precision_policy=DefaultConfig.default_precision_policy,
@@ -118,8 +116,11 @@ class IncompressibleNavierStokesStepper(Stepper):
                 precision_policy=DefaultConfig.default_precision_policy,
                 compute_backend=DefaultConfig.default_backend,
             )
+            kw = {}
+            if grid is not None and grid.nDevices > 1:
+                kw = dict(start_index=grid.start_index, global_shape=grid.shape)
             for bc in bc_with_vertices:
-                bc_mask, missing_mask = mesh_masker(bc, bc_mask, missing_mask)
+                bc_mask, missing_mask = mesh_masker(bc, bc_mask, missing_mask, **kw)
         return bc_mask, missing_mask
 
     @staticmethod
