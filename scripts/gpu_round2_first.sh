@@ -30,6 +30,27 @@ run --lattice D3Q27 --collision SmagorinskyLESBGK --config periodic
 run --lattice D3Q27 --collision KBC --config periodic --force 1e-6
 run --collision SmagorinskyLESBGK --policy FP32FP16
 run --config periodic --force 1e-6 --policy FP64FP64 --n 384
+# small grids: the user loop vs stepper.run (CUDA graph of a pair of steps)
+python - <<'PY' 2>&1 | tee gpurun_out/r2_small_grids.log
+import sys, time, torch
+sys.path.insert(0, ".")
+import bench
+for n in (64, 128, 256):
+    sys.argv = ["bench.py", "--n", str(n)]
+    args = bench.parse()
+    grid, stepper = bench.build_case(args, (n, n, n))
+    f_0, f_1, bm, mm = stepper.prepare_fields()
+    steps = 2000
+    for label, fn in (("loop ", None), ("graph", True)):
+        torch.cuda.synchronize(); t = time.perf_counter()
+        if fn is None:
+            for i in range(steps):
+                f_0, f_1 = stepper(f_0, f_1, bm, mm, 1.0, i); f_0, f_1 = f_1, f_0
+        else:
+            f_0, f_1 = stepper.run(f_0, f_1, bm, mm, 1.0, steps)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t
+        print(f"{n}^3 {label}: {n**3 * steps / dt / 1e9:.1f} GLUPS ({dt / steps * 1e6:.1f} us/step)")
+PY
 # one full capture of the lean KBC kernel for the register / stall picture
 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 4 -c 1 -o gpurun_out/r2_kbc_lean python bench.py --n 256 --lattice D3Q27 --collision KBC --cells-per-thread 301 --steps 3 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/r2_ncu_lean.log 2>&1
 ncu -i gpurun_out/r2_kbc_lean.ncu-rep --page raw --csv > gpurun_out/r2_kbc_lean_raw.csv 2>/dev/null && rm -f gpurun_out/r2_kbc_lean.ncu-rep

@@ -163,6 +163,30 @@ report("windtunnel", windtunnel)
 """
 
 
+GRAPH_GROUP = PRELUDE + r"""
+import time
+
+def graph_run(name, n):
+    g = load_golden(name)
+    stepper, f_0, f_1, bm, mm = native_case(g)
+    a, b = stepper.run(f_0, f_1, bm, mm, g["omega"], n)                 # captured pair of steps, replayed
+    stepper2, g_0, g_1, bm2, mm2 = native_case(g)
+    for i in range(n):
+        g_0, g_1 = stepper2(g_0, g_1, bm2, mm2, g["omega"], i)
+        g_0, g_1 = g_1, g_0
+    same = bool(torch.equal(a, g_0))
+    a, b = stepper.run(a, b, bm, mm, g["omega"], n)                     # second call: same buffers (n even) -> replay only
+    for i in range(n):
+        g_0, g_1 = stepper2(g_0, g_1, bm2, mm2, g["omega"], i)
+        g_0, g_1 = g_1, g_0
+    return same and bool(torch.equal(a, g_0))
+
+for name, n in %(cases)r:
+    report("%%s|%%d" %% (name, n), lambda: graph_run(name, n))
+"""
+GRAPH_CASES = [("cavity_d3q19_bgk_fp32", 10), ("cavity_d3q19_bgk_fp32fp16", 10), ("sphere_d3q27_kbc_fp32", 12), ("cavity_d2q9_kbc_fp32", 7)]
+
+
 @functools.lru_cache(maxsize=None)
 def run_group(script, timeout=900):
     """Run one child; returns ({case key: status line}, tail of its output).  Never raises."""
@@ -221,6 +245,12 @@ def test_first_run_of_the_lean_kbc_variant(name, backend, v):
 def test_first_run_of_the_extended_collision_operators(lattice):
     """xlbn_collide_ext / xlbn_exact_difference through the operator classes vs the numpy oracle on random states."""
     check(OPS_GROUP % {"root": ROOT}, lattice)
+
+
+@pytest.mark.parametrize("name,n", GRAPH_CASES)
+def test_first_run_of_the_cuda_graph_loop(name, n):
+    """stepper.run(n): a captured pair of steps replayed n/2 times must give the bits of n individual calls."""
+    check(GRAPH_GROUP % {"root": ROOT, "cases": GRAPH_CASES}, f"{name}|{n}")
 
 
 def mesh_keys():

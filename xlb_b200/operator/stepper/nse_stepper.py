@@ -211,6 +211,47 @@ class IncompressibleNavierStokesStepper(Stepper):
         self._halo_step += 1
         return f_0, f_1
 
+    def run(self, f_0, f_1, bc_mask, missing_mask, omega, n_steps, timestep=0, use_graph=True):
+        """`n_steps` time steps with the buffer swap done here: the user loop of examples/performance/mlups_3d.py:77-80,
+        ``for i in range(n): f_0, f_1 = stepper(f_0, f_1, ...); f_0, f_1 = f_1, f_0``, as one call.  Returns ``(f_0, f_1)``
+        after the last swap, i.e. ``f_0`` holds the newest populations.
+
+        Not part of the reference API.  It exists for small grids, where a step is a few tens of microseconds and the
+        per-launch cost on the host shows: a PAIR of steps (f_0 -> f_1 -> f_0) is captured once into a CUDA graph and replayed
+        ``n_steps // 2`` times; an odd last step is launched directly.  Single-device grids only; ``omega`` is baked into the
+        captured launches, so a different omega (or different buffers) re-captures."""
+        if self.grid is not None and self.grid.nDevices > 1:
+            raise NotImplementedError("run(): single-device grids only; call the stepper per step on a slab grid")
+        n_steps = int(n_steps)
+        if n_steps <= 0:
+            return f_0, f_1
+        pairs = n_steps // 2
+        if use_graph and pairs >= 2:
+            key = (f_0.data_ptr(), f_1.data_ptr(), bc_mask.data_ptr(), missing_mask.data_ptr(), missing_mask._version, float(omega), tuple(f_0.shape))
+            if getattr(self, "_graph_key", None) != key:
+                # two plain steps first: handle creation, bitmask packing and the EquilibriumBC constants (which synchronise) must
+                # not happen inside a capture
+                self._step(f_0, f_1, bc_mask, missing_mask, omega, timestep)
+                self._step(f_1, f_0, bc_mask, missing_mask, omega, timestep + 1)
+                pairs -= 1
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._step(f_0, f_1, bc_mask, missing_mask, omega, timestep)
+                    self._step(f_1, f_0, bc_mask, missing_mask, omega, timestep + 1)
+                pairs -= 1  # the capture pass above does not execute; replay it once for the pair it stands for
+                graph.replay()
+                self._graph, self._graph_key = graph, key
+            for _ in range(pairs):
+                self._graph.replay()
+        else:
+            for i in range(pairs):
+                self._step(f_0, f_1, bc_mask, missing_mask, omega, timestep + 2 * i)
+                self._step(f_1, f_0, bc_mask, missing_mask, omega, timestep + 2 * i + 1)
+        if n_steps % 2:
+            self._step(f_0, f_1, bc_mask, missing_mask, omega, timestep + n_steps - 1)
+            return f_1, f_0
+        return f_0, f_1
+
     def reset_halo(self):
         """Re-prime the ghost planes from the populations passed to the next call (use after modifying the populations
         outside the stepper on a slab grid).  Collective: synchronises the device and all ranks, then skips two halo
