@@ -21,6 +21,7 @@ run --lattice D3Q27 --collision KBC --policy FP32FP16
 run --lattice D3Q27 --collision KBC --policy FP32FP16 --cells-per-thread 301
 # wind tunnel with a mesh body (N3): voxelisation + 200 steps
 timeout 300 python examples/windtunnel_mesh.py 256 96 96 200 2>&1 | tail -14 | tee gpurun_out/r2_windtunnel_mesh.log
+timeout 300 python examples/turbulent_channel.py 32 400 2>&1 | tail -8 | tee gpurun_out/r2_turbulent_channel.log
 # extended collision kernels (N4): first numbers
 run --collision SmagorinskyLESBGK
 run --collision SmagorinskyLESBGK --config periodic

@@ -33,7 +33,7 @@ EXTRA_CASES_2D = ["channel2d_d2q9_bgk_outflow_fp32", "channel2d_d2q9_bgk_zouhe_p
 EXTRA_CASES_POLICIES = ["sphere_d3q19_bgk_fp32fp16", "sphere_d3q27_kbc_fp64fp32", "sphere_d3q27_kbc_zouhe_pressure_fp64"]
 LATE_CASES = EXTRA_CASES_2D + EXTRA_CASES_POLICIES
 # Produced by the reference's WARP backend itself, executed per cell under oracle/refshim's interpretive `warp`
-# (tests/golden/make_golden_warp.py).  All FP32FP32.
+# (tests/golden/make_golden_warp.py).  FP32FP32 (one FP64FP64 case among the N4 ones).
 WARP_CASES = [
     "warp_cavity_d3q19_bgk",
     "warp_cavity_d3q19_bgk_solid255",
@@ -56,6 +56,7 @@ WARP_CASES_N4 = [  # one per extended instantiation of the fused kernel (csrc/st
     "warp_periodic_d3q27_smagorinsky_forced",
     "warp_periodic_d2q9_bgk_forced",
     "warp_periodic_d2q9_kbc_forced",
+    "warp_channel_d3q27_kbc_forced_fp64",  # examples/cfd/turbulent_channel_3d.py in small: KBC + force + Regularized no-slip walls, FP64FP64
 ]
 # relative tolerance (max |a-b| / max |b|) per store/compute policy; north-star: 1e-5 fp32, 1e-3 fp16 storage
 RTOL = {"FP32FP32": 1e-5, "FP64FP32": 1e-5, "FP64FP64": 1e-9, "FP32FP16": 1e-3, "FP64FP16": 1e-3}

@@ -14,7 +14,9 @@ interior flag of the Warp masker, the Warp outflow neighbour read, and Smagorins
 
 File format = make_golden.py's (tests/common.py:load_golden), plus `backend="WARP"`, optional `solid255` (cells whose
 bc_mask was set to 255 after prepare_fields, as MeshBoundaryMasker does for solid interiors), optional `smagorinsky`.
-FP32FP32 only: under Warp's typing rules the FP16 / FP64 mixes depend on conversions the stand-in does not model.
+FP32FP32, plus one FP64FP64 case (with omega representable in float32: Warp types a Python float handed to a launch as
+float32, so any other omega would be rounded there before the kernel widens it); the mixed policies depend on implicit
+conversions of Warp that the stand-in does not model.
 """
 
 import os
@@ -58,7 +60,9 @@ VS = {"D2Q9": xlb.velocity_set.D2Q9, "D3Q19": xlb.velocity_set.D3Q19, "D3Q27": x
 POLICY = "FP32FP32"
 
 
-def init(lattice):
+def init(lattice, policy="FP32FP32"):
+    global POLICY
+    POLICY = policy
     pp = PrecisionPolicy[POLICY]
     # one case per "process": the Warp stepper looks outflow ids up in the GLOBAL registry (nse_stepper.py:254-259), so ids of an
     # earlier case must not linger
@@ -92,15 +96,16 @@ def run_and_save(name, meta, stepper, bcs_meta, steps, omega, d, f_init=None, so
         i, b = inlet
         idx = bcs_meta[i]["indices"]
         idx3 = tuple(idx) if len(idx) == 3 else (idx[0], idx[1], np.zeros_like(idx[0]))
-        pv = np.zeros((d,) + tuple(np.asarray(f_0).shape[2:]), np.float32)  # same container as the JAX-path fixtures: [d, ny, nz]
+        pv = np.zeros((d,) + tuple(np.asarray(f_0).shape[2:]), np.asarray(f_1).dtype)  # same container as the JAX-path fixtures: [d, ny, nz]
         pv[0][idx3[1:]] = np.asarray(f_1)[0][idx3]
         bcs_meta[i]["prescribed"] = pv if d == 3 else pv[:, :, 0]
     start = np.asarray(f_0).copy()
     for i in range(steps):
         f_0, f_1 = stepper(f_0, f_1, bc_mask, missing, omega, i)
         f_0, f_1 = f_1, f_0
-    rho = wp.zeros((1,) + f_0.shape[1:], dtype=wp.float32)
-    u = wp.zeros((3,) + f_0.shape[1:], dtype=wp.float32) if d == 3 else None
+    cdt = wp.float64 if POLICY.startswith("FP64") else wp.float32
+    rho = wp.zeros((1,) + f_0.shape[1:], dtype=cdt)
+    u = wp.zeros((3,) + f_0.shape[1:], dtype=cdt) if d == 3 else None
     out = dict(meta)
     out.update(steps=steps, omega=omega, n_bc=len(bcs_meta), backend="WARP", policy=POLICY)
     for i, b in enumerate(bcs_meta):
@@ -229,6 +234,26 @@ def periodic(name, lattice, shape, steps, collision, omega, force=None):
     run_and_save(name, meta, stepper, [], steps, omega, vs.d, f_init=np.asarray(f_init))
 
 
+def channel(name, shape, steps, omega, force):
+    """examples/cfd/turbulent_channel_3d.py:60-135 in small: periodic in x and y, RegularizedBC("velocity", (0, 0, 0)) on the
+    two z faces without their edges, KBC + body force (ForcedCollision / ExactDifference), FP64FP64, seeded random start
+    through helper.initialize_eq(u=...)."""
+    from xlb.helper import initialize_eq
+
+    vs, pp = init("D3Q27", "FP64FP64")
+    grid = grid_factory(shape)
+    box = grid.bounding_box_indices(remove_edges=True)
+    walls = [box["bottom"][i] + box["top"][i] for i in range(vs.d)]
+    bcs = [RegularizedBC("velocity", prescribed_value=(0.0, 0.0, 0.0), indices=walls)]
+    stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=bcs, collision_type="KBC", force_vector=np.asarray(force, dtype=np.float64))
+    np.random.seed(0)
+    u_init = wp.array(1e-2 * np.random.random((vs.d,) + tuple(shape)), dtype=wp.float64)
+    f_init = initialize_eq(wp.zeros((vs.q,) + tuple(shape), dtype=wp.float64), grid, vs, pp, BE, u=u_init)
+    meta = [dict(kind="regularized", id=bcs[0].id, indices=np.array(walls), bc_type="velocity")]  # `prescribed` filled from f_1[0]
+    run_and_save(name, dict(lattice="D3Q27", collision="KBC", shape=np.array(shape), force_vector=np.asarray(force, dtype=np.float64)), stepper, meta,
+                 steps, omega, vs.d, f_init=np.asarray(f_init), inlet=(0, bcs[0]))  # fmt: skip
+
+
 def mesh_shapes():
     """Small closed triangle soups at generic (non-lattice-aligned) positions: a tetrahedron, a rotated box, an octahedron."""
     tet = np.array([[2.21, 1.37, 1.11], [9.63, 3.19, 2.87], [5.02, 9.43, 3.33], [5.57, 4.21, 8.79]])
@@ -302,6 +327,8 @@ if __name__ == "__main__":
         periodic("warp_periodic_d3q27_kbc_forced", "D3Q27", (6, 8, 6), 8, "KBC", 1.8, force=(-1e-5, 0.0, 2e-5))
     if want("warp_periodic_d2q9_bgk_forced"):
         periodic("warp_periodic_d2q9_bgk_forced", "D2Q9", (12, 10), 12, "BGK", 1.5, force=(2e-5, -1e-5))
+    if want("warp_channel_d3q27_kbc_forced_fp64"):
+        channel("warp_channel_d3q27_kbc_forced_fp64", (10, 8, 9), 12, 1.75, (3e-6, 0.0, 0.0))
     for body in ("tetrahedron", "box", "octahedron"):
         for lattice in ("D3Q19", "D3Q27"):
             n = f"warp_mesh_{body}_{lattice.lower()}"

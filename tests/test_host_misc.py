@@ -69,7 +69,7 @@ def test_warp_and_jax_standins_are_installed_only_when_missing():
     assert np.allclose(jnp.maximum(0.0, np.array([-1.0, 2.0])), [0.0, 2.0])
 
 
-@pytest.mark.parametrize("script", ["examples/cavity_mlups.py", "examples/sphere_kbc.py", "examples/cavity_2d.py", "examples/windtunnel_mesh.py", "bench.py", "__graft_entry__.py", "scripts/mgpu_check.py"])
+@pytest.mark.parametrize("script", ["examples/cavity_mlups.py", "examples/sphere_kbc.py", "examples/cavity_2d.py", "examples/windtunnel_mesh.py", "examples/turbulent_channel.py", "bench.py", "__graft_entry__.py", "scripts/mgpu_check.py"])
 def test_scripts_compile(script):
     py_compile.compile(os.path.join(ROOT, script), doraise=True)
 
