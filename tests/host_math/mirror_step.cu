@@ -2,8 +2,9 @@
 // store_cells and the cell algebra they inline) compiled for the HOST and driven by plain loops instead of a CUDA launch.
 // The loops below do what step_kernel's prologue does (thread coordinates -> x, y, z0; x-plane class); everything else —
 // pointer tables, pull addressing incl. periodic wrap and ghost planes, boundary dispatch, collision, stores incl. the
-// peer-plane stores — is the shipped code.  Not covered: the packed-pair / half2 paths (device intrinsics), launch
-// geometry, and anything that only exists on a GPU (coalescing, races).
+// peer-plane stores — is the shipped code, incl. the packed-pair path (cells_per_thread 102) and the half2-state path (202),
+// whose packed instructions and warp votes have one-lane host twins (common.cuh).  Not covered: launch geometry and anything
+// that only exists on a GPU (coalescing, scheduling, races).
 // Built by tests/test_host_mirror_step.py: one object per lattice (-DMIRROR_LATTICE=0|1|2, compiled in parallel) + error.cu,
 // linked into tests/host_math/_build/libmirror_step.so.
 #define XLBN_HOST_MIRROR 1
@@ -34,9 +35,51 @@ int host_step(const StepCall& c) {
   return 0;
 }
 
+// MODE 1 (packed fp32x2 pair path, two cells per thread) and MODE 2 (half2-state pair path): the other bodies of step_kernel
+template <class L, int COLL, class TS, int MODE>
+int host_step_pair(const StepCall& c) {
+  StepParams<TS> p;
+  if (int e = fill_step_params<L, TS>(c, p)) return e;
+  if (c.nz % 2) return fail(XLBN_E_SHAPE, "mirror: pair paths need an even nz");
+  if constexpr (MODE == 2) {  // what bc_precompute_kernel does on the device: EquilibriumBC cells' constant update
+    BcEntry* table = c.table_rw;
+    for (int id = 0; id < 256; ++id) {
+      if (table[id].kind != XLBN_BC_EQUILIBRIUM) continue;
+      float u[L::D], f[L::Q];
+      XLBN_FOR(L::D, d) u[d] = (float)table[id].u[d]; XLBN_END
+      equilibrium<L, float>((float)table[id].rho, u, f);
+      collide_cell<L, COLL, float, kFast<COLL, float>>(f, (float)c.omega);
+      XLBN_FOR(L::Q, l) table[id].eq_out[l] = f[l]; XLBN_END
+    }
+  }
+  for (int x = c.x_begin; x < c.x_begin + c.x_count; ++x) {
+    const bool first = (x == 0), last = (x == p.nx - 1);
+    for (int y = 0; y < p.ny; ++y)
+      for (int z0 = 0; z0 < p.nz; z0 += 2) {
+        if constexpr (MODE == 1) {
+          if (!first && !last) step_body_pk<L, COLL, TS, 2, 0>(p, x, y, z0);
+          else if (first && !last) step_body_pk<L, COLL, TS, 2, 1>(p, x, y, z0);
+          else if (last && !first) step_body_pk<L, COLL, TS, 2, 2>(p, x, y, z0);
+          else step_body_pk<L, COLL, TS, 2, 3>(p, x, y, z0);
+        } else {
+          if (!first && !last) step_body_h2<L, 0>(p, x, y, z0);
+          else if (first && !last) step_body_h2<L, 1>(p, x, y, z0);
+          else if (last && !first) step_body_h2<L, 2>(p, x, y, z0);
+          else step_body_h2<L, 3>(p, x, y, z0);
+        }
+      }
+  }
+  return 0;
+}
+
 template <class L, int COLL, class TC, class TS>
 int host_step_v(const StepCall& c) {
   if (c.requested_v == 1) return host_step<L, COLL, TC, TS, 1>(c);
+  if constexpr (!kExtCollision<COLL> && sizeof(TC) == 4) {
+    if (c.requested_v == 102) return host_step_pair<L, COLL, TS, 1>(c);
+    if constexpr (sizeof(TS) == 2 && COLL == XLBN_BGK)
+      if (c.requested_v == 202) return host_step_pair<L, COLL, TS, 2>(c);
+  }
   if constexpr (!kExtCollision<COLL>) {  // the library builds the extended operators with one cell per thread only
     if (c.requested_v == 2) return host_step<L, COLL, TC, TS, 2>(c);
     if constexpr (sizeof(TS) <= 4)

@@ -468,24 +468,24 @@ XLBN_DEV void step_body(const StepParams<TS>& p, const int x, const int y, const
 
 // ---- packed pair path: two neighbouring cells per fp32x2 register pair (FADD2 / FMUL2 / FFMA2) ---------------------
 template <class TS>
-XLBN_DEVONLY f32x2 pair_up(TS lo, TS hi);
+XLBN_DEV f32x2 pair_up(TS lo, TS hi);
 template <>
-XLBN_DEVONLY f32x2 pair_up<float>(float lo, float hi) { return f32x2(lo, hi); }
+XLBN_DEV f32x2 pair_up<float>(float lo, float hi) { return f32x2(lo, hi); }
 template <>
-XLBN_DEVONLY f32x2 pair_up<__half>(__half lo, __half hi) { return f32x2(__half22float2(__halves2half2(lo, hi))); }
+XLBN_DEV f32x2 pair_up<__half>(__half lo, __half hi) { return f32x2(__half22float2(__halves2half2(lo, hi))); }
 template <class TS>
-XLBN_DEVONLY void pair_down(f32x2 v, TS& lo, TS& hi);
+XLBN_DEV void pair_down(f32x2 v, TS& lo, TS& hi);
 template <>
-XLBN_DEVONLY void pair_down<float>(f32x2 v, float& lo, float& hi) { lo = v.v.x; hi = v.v.y; }
+XLBN_DEV void pair_down<float>(f32x2 v, float& lo, float& hi) { lo = v.v.x; hi = v.v.y; }
 template <>
-XLBN_DEVONLY void pair_down<__half>(f32x2 v, __half& lo, __half& hi) {
+XLBN_DEV void pair_down<__half>(f32x2 v, __half& lo, __half& hi) {
   const __half2 h = __float22half2_rn(v.v);
   lo = __low2half(h);
   hi = __high2half(h);
 }
 
 template <class L, int COLL, class TS, int V, int XC>
-XLBN_DEVONLY void step_body_pk(const StepParams<TS>& p, const int x, const int y, const int z0) {
+XLBN_DEV void step_body_pk(const StepParams<TS>& p, const int x, const int y, const int z0) {
   static_assert(V % 2 == 0, "pair path needs an even number of cells per thread");
   constexpr int Q = L::Q, NP = V / 2;
   const unsigned nz = (unsigned)p.nz;
@@ -576,7 +576,7 @@ __global__ void bc_precompute_kernel(BcEntry* table, float omega) {
 // FullwayBounceBack (bit copy of the opposite population's half; fp16 -> fp32 -> fp16 is exact) and EquilibriumBC cells
 // (the precomputed constant update, BcEntry::eq_out); id_lo / id_hi = bc ids of the two cells.
 template <class L, int XC, bool WITH_BC>
-XLBN_DEVONLY void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L::Q], const unsigned cell, const int id_lo, const int id_hi) {
+XLBN_DEV void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L::Q], const unsigned cell, const int id_lo, const int id_hi) {
   using TS = __half;
   constexpr int Q = L::Q;
   bool eq_lo = false, eq_hi = false, fw_lo = false, fw_hi = false;
@@ -647,7 +647,7 @@ XLBN_DEVONLY void h2_collide_store(const StepParams<__half>& p, const __half2 (&
 // so the kernel keeps the residency of the one-cell path while issuing ~2.5x fewer instructions per cell (FADD2 / FMUL2 /
 // FFMA2 for both cells at once); the fp16 path is issue-bound otherwise (profiles/README.md).
 template <class L, int XC>
-XLBN_DEVONLY void step_body_h2(const StepParams<__half>& p, const int x, const int y, const int z0) {
+XLBN_DEV void step_body_h2(const StepParams<__half>& p, const int x, const int y, const int z0) {
   using TS = __half;
   constexpr int Q = L::Q, V = 2;
   const unsigned nz = (unsigned)p.nz;
@@ -691,15 +691,15 @@ XLBN_DEVONLY void step_body_h2(const StepParams<__half>& p, const int x, const i
   //   anything else (other BC kinds, solid cells)       -> per-thread: pair path or scalar boundary tail
   const int k0 = ids.v[0] ? (int)p.kinds[ids.v[0]] : 0, k1 = ids.v[1] ? (int)p.kinds[ids.v[1]] : 0;
   const auto simple = [](int id, int k) { return id != 255 && (k == XLBN_BC_NONE || k == XLBN_BC_FULLWAY_BOUNCE_BACK || k == XLBN_BC_EQUILIBRIUM); };
-  const unsigned active = __activemask();
-  const bool warp_any_bc = __any_sync(active, any_bc);
+  const unsigned active = XLBN_ACTIVEMASK();
+  const bool warp_any_bc = XLBN_ANY(active, any_bc);
   if (!warp_any_bc) {
     __half2 h[Q];
     load_all(h);
     h2_collide_store<L, XC, false>(p, h, cell, 0, 0);
     return;
   }
-  if (__all_sync(active, simple(ids.v[0], k0) && simple(ids.v[1], k1))) {
+  if (XLBN_ALL(active, simple(ids.v[0], k0) && simple(ids.v[1], k1))) {
     __half2 h[Q];
     load_all(h);
     h2_collide_store<L, XC, true>(p, h, cell, ids.v[0], ids.v[1]);
