@@ -5,11 +5,12 @@
 // peer-plane stores — is the shipped code, incl. the packed-pair path (cells_per_thread 102) and the half2-state path (202),
 // whose packed instructions and warp votes have one-lane host twins (common.cuh).  Not covered: launch geometry and anything
 // that only exists on a GPU (coalescing, scheduling, races).
-// Built by tests/test_host_mirror_step.py: one object per lattice (-DMIRROR_LATTICE=0|1|2, compiled in parallel) + error.cu,
-// linked into tests/host_math/_build/libmirror_step.so.
+// Built by tests/test_host_mirror_step.py: one object per (lattice, collision) — -DMIRROR_LAT=D3Q27 -DMIRROR_TAG=XLBN_D3Q27
+// -DMIRROR_COLL=5 -DMIRROR_NAME=mirror_step_2_5, compiled in parallel — plus error.cu, linked into
+// tests/host_math/_build/libmirror_step.so.
 #define XLBN_HOST_MIRROR 1
-#ifndef MIRROR_LATTICE
-#error "compile with -DMIRROR_LATTICE=0 (D2Q9), 1 (D3Q19), 2 (D3Q27 BGK/KBC) or 3 (D3Q27 extended operators)"
+#if !defined(MIRROR_LAT) || !defined(MIRROR_TAG) || !defined(MIRROR_COLL) || !defined(MIRROR_NAME)
+#error "compile with -DMIRROR_LAT=<lattice type> -DMIRROR_TAG=<xlbn_lattice> -DMIRROR_COLL=<collision code> -DMIRROR_NAME=<symbol>"
 #endif
 #include "../../xlb_b200/csrc/step_kernel.cuh"
 
@@ -102,21 +103,14 @@ int host_step_policy(const StepCall& c) {
 
 extern "C" {
 
-#if MIRROR_LATTICE == 0
+#ifdef MIRROR_DEFINE_ERROR
 const char* mirror_last_error(void) { return error_buffer(); }
-#define MIRROR_STEP mirror_step_d2q9
-#elif MIRROR_LATTICE == 1
-#define MIRROR_STEP mirror_step_d3q19
-#elif MIRROR_LATTICE == 2
-#define MIRROR_STEP mirror_step_d3q27
-#else
-#define MIRROR_STEP mirror_step_d3q27_ext
 #endif
 
 // One step of the fused kernel's source on the host.  Arguments as xlbn_step + xlbn_stepper_desc, flattened; all pointers are
 // HOST pointers.  dims are the KERNEL extents (2-D: (1, nx, ny), as xlbn_step passes them).  bc_kind / bc_rho / bc_u: 256-entry
 // tables indexed by bc id.  ghost_* / out_*: x-slab ghost planes as in xlbn_step's halo (NULL: periodic in x).
-int MIRROR_STEP(int lattice, int collision, int compute_dtype, int store_dtype, int cells_per_thread, const void* f0, void* f1, const uint8_t* bc_mask,
+int MIRROR_NAME(int lattice, int collision, int compute_dtype, int store_dtype, int cells_per_thread, const void* f0, void* f1, const uint8_t* bc_mask,
                 const uint32_t* missing_bits, const int32_t* bc_kind, const double* bc_rho, const double* bc_u, const int32_t dims[3], int x_begin,
                 int x_count, double omega, const double* force, double smagorinsky, const void* ghost_lo, const void* ghost_hi, void* out_lo,
                 void* out_hi) {
@@ -154,31 +148,7 @@ int MIRROR_STEP(int lattice, int collision, int compute_dtype, int store_dtype, 
   c.out_hi = out_hi;
   for (int a = 0; a < 3; ++a) c.force[a] = force ? force[a] : 0.0;
   c.smagorinsky = smagorinsky;
-  constexpr int F = XLBN_COLLISION_FORCED;
-#define CASE(LAT, TAG, COLL) \
-  if (lattice == TAG && collision == (COLL)) return host_step_policy<LAT, (COLL)>(c);
-#if MIRROR_LATTICE == 1
-  CASE(D3Q19, XLBN_D3Q19, XLBN_BGK)
-  CASE(D3Q19, XLBN_D3Q19, XLBN_BGK | F)
-  CASE(D3Q19, XLBN_D3Q19, XLBN_SMAGORINSKY_LES_BGK)
-  CASE(D3Q19, XLBN_D3Q19, XLBN_SMAGORINSKY_LES_BGK | F)
-#elif MIRROR_LATTICE == 2
-  CASE(D3Q27, XLBN_D3Q27, XLBN_BGK)
-  CASE(D3Q27, XLBN_D3Q27, XLBN_KBC)
-#elif MIRROR_LATTICE == 3
-  CASE(D3Q27, XLBN_D3Q27, XLBN_BGK | F)
-  CASE(D3Q27, XLBN_D3Q27, XLBN_KBC | F)
-  CASE(D3Q27, XLBN_D3Q27, XLBN_SMAGORINSKY_LES_BGK)
-  CASE(D3Q27, XLBN_D3Q27, XLBN_SMAGORINSKY_LES_BGK | F)
-  CASE(D3Q27, XLBN_D3Q27, XLBN_KBC | kLeanKbc)
-#else
-  CASE(D2Q9, XLBN_D2Q9, XLBN_BGK)
-  CASE(D2Q9, XLBN_D2Q9, XLBN_KBC)
-  CASE(D2Q9, XLBN_D2Q9, XLBN_BGK | F)
-  CASE(D2Q9, XLBN_D2Q9, XLBN_KBC | F)
-  CASE(D2Q9, XLBN_D2Q9, XLBN_KBC | kLeanKbc)
-#endif
-#undef CASE
+  if (lattice == MIRROR_TAG && collision == (MIRROR_COLL)) return host_step_policy<MIRROR_LAT, (MIRROR_COLL)>(c);
   return fail(XLBN_E_ARG, "mirror: lattice %d / collision %d is not built", lattice, collision);
 }
 

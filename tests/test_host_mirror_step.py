@@ -27,6 +27,9 @@ CSRC = os.path.join(ROOT, "xlb_b200", "csrc")
 LATTICE = {"D2Q9": 0, "D3Q19": 1, "D3Q27": 2}
 COLLISION = {"BGK": 0, "KBC": 1, "SmagorinskyLESBGK": 2}
 DTYPE = {np.dtype(np.float16): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}
+# (lattice, collision code) pairs the library instantiates: base | 4 = forced (XLBN_COLLISION_FORCED), | 8 = lean KBC (kLeanKbc)
+PARTS = [("D3Q19", 0), ("D3Q19", 4), ("D3Q19", 2), ("D3Q19", 6), ("D3Q27", 0), ("D3Q27", 1), ("D3Q27", 4), ("D3Q27", 5), ("D3Q27", 2), ("D3Q27", 6),
+         ("D3Q27", 9), ("D2Q9", 0), ("D2Q9", 1), ("D2Q9", 4), ("D2Q9", 5), ("D2Q9", 9)]  # fmt: skip
 
 
 @pytest.fixture(scope="module")
@@ -38,20 +41,27 @@ def mirror():
         build = os.path.dirname(OUT)
         os.makedirs(build, exist_ok=True)
         base = ["nvcc", "-std=c++17", "-O0", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
-        jobs = [(base + ["-c", os.path.join(CSRC, "error.cu"), "-o", os.path.join(build, "error.o")])]
-        jobs += [base + [f"-DMIRROR_LATTICE={k}", "-c", SRC, "-o", os.path.join(build, f"mirror_step_{k}.o")] for k in range(4)]
-        procs = [subprocess.Popen(j, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for j in jobs]  # one object per lattice, in parallel
-        for p in procs:
+        jobs = [base + ["-c", os.path.join(CSRC, "error.cu"), "-o", os.path.join(build, "error.o")]]
+        objs = [os.path.join(build, "error.o")]
+        for i, (lat, coll) in enumerate(PARTS):  # one object per (lattice, collision), compiled in parallel
+            obj = os.path.join(build, f"mirror_step_{LATTICE[lat]}_{coll}.o")
+            flags = [f"-DMIRROR_LAT={lat}", f"-DMIRROR_TAG=XLBN_{lat}", f"-DMIRROR_COLL={coll}", f"-DMIRROR_NAME=mirror_step_{LATTICE[lat]}_{coll}"]
+            jobs.append(base + flags + (["-DMIRROR_DEFINE_ERROR"] if i == 0 else []) + ["-c", SRC, "-o", obj])
+            objs.append(obj)
+        running, pending = [], list(jobs)
+        while pending or running:
+            while pending and len(running) < (os.cpu_count() or 4):
+                running.append(subprocess.Popen(pending.pop(0), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+            p = running.pop(0)
             log = p.communicate()[0]
             assert p.returncode == 0, log[-3000:]
-        objs = [os.path.join(build, "error.o")] + [os.path.join(build, f"mirror_step_{k}.o") for k in range(4)]
         proc = subprocess.run(["nvcc", "-shared", "-o", OUT] + objs, capture_output=True, text=True)
         assert proc.returncode == 0, proc.stderr[-3000:]
     lib = C.CDLL(OUT)
     lib.mirror_last_error.restype = C.c_char_p
     P, I, D = C.c_void_p, C.c_int, C.c_double
-    for name in ("mirror_step_d2q9", "mirror_step_d3q19", "mirror_step_d3q27", "mirror_step_d3q27_ext"):
-        getattr(lib, name).argtypes = [I, I, I, I, I, P, P, P, P, P, P, P, P, I, I, D, P, D, P, P, P, P]
+    for lat, coll in PARTS:
+        getattr(lib, f"mirror_step_{LATTICE[lat]}_{coll}").argtypes = [I, I, I, I, I, P, P, P, P, P, P, P, P, I, I, D, P, D, P, P, P, P]
     return lib
 
 
@@ -76,8 +86,7 @@ def mirror_run(lib, g, steps=None, v=1, lean_kbc=False, masks=None):
     if g["force_vector"] is not None:
         force[: lat.d] = g["force_vector"]
     for _ in range(g["steps"] if steps is None else steps):
-        fn = getattr(lib, "mirror_step_" + g["lattice"].lower() + ("_ext" if g["lattice"] == "D3Q27" and coll > 1 else ""))
-        rc = fn(LATTICE[g["lattice"]], coll, DTYPE[np.dtype(cdt)], DTYPE[np.dtype(sdt)], v, fa.ctypes.data, fb.ctypes.data, bm.ctypes.data,
+        rc = getattr(lib, f"mirror_step_{LATTICE[g['lattice']]}_{coll}")(LATTICE[g["lattice"]], coll, DTYPE[np.dtype(cdt)], DTYPE[np.dtype(sdt)], v, fa.ctypes.data, fb.ctypes.data, bm.ctypes.data,
                              bits.ctypes.data, kind.ctypes.data, rho.ctypes.data, u.ctypes.data, C.cast(dims, C.c_void_p), 0, dims[0], g["omega"],
                              force.ctypes.data, g["smagorinsky"], None, None, None, None)  # fmt: skip
         assert rc == 0, lib.mirror_last_error().decode()
@@ -133,7 +142,7 @@ def mirror_run_slabs(lib, g, n_slabs, steps):
     force = np.zeros(3)
     if g["force_vector"] is not None:
         force[: lat.d] = g["force_vector"]
-    fn = getattr(lib, "mirror_step_" + g["lattice"].lower() + ("_ext" if g["lattice"] == "D3Q27" and coll > 1 else ""))
+    fn = getattr(lib, f"mirror_step_{LATTICE[g['lattice']]}_{coll}")
     for t in range(steps):
         pin, pout = t & 1, (t + 1) & 1
         for r in range(n_slabs):
