@@ -137,3 +137,38 @@ def test_read_stl_binary_and_ascii(tmp_path):
     bad.write_text("hello")
     with pytest.raises(ValueError):
         read_stl(str(bad))
+
+
+def test_mesh_boundary_masker_argument_checks_mirror_the_reference():
+    """mesh_boundary_masker.py:27-28 (2-D), L199-216 (vertices / indices / (N, 3) / mesh inside the domain) — checked before
+    anything touches the device, in the reference's order; and there is no CPU fallback behind them."""
+    import torch
+
+    import xlb_b200 as xlb
+    from xlb_b200.compute_backend import ComputeBackend
+    from xlb_b200.operator.boundary_condition import HalfwayBounceBackBC
+    from xlb_b200.operator.boundary_masker import MeshBoundaryMasker
+
+    pp, be = xlb.PrecisionPolicy.FP32FP32, ComputeBackend.WARP
+    xlb.init(velocity_set=xlb.velocity_set.D2Q9(pp, be), default_backend=be, default_precision_policy=pp)
+    with pytest.raises(NotImplementedError, match="not implemented in 2D"):
+        MeshBoundaryMasker()
+    vs = xlb.velocity_set.D3Q19(pp, be)
+    xlb.init(velocity_set=vs, default_backend=be, default_precision_policy=pp)
+    with pytest.raises(ValueError, match="edge_test"):
+        MeshBoundaryMasker(edge_test="sat")
+    masker = MeshBoundaryMasker()
+    bc_mask, missing = torch.zeros(1, 8, 8, 8, dtype=torch.uint8), torch.zeros(19, 8, 8, 8, dtype=torch.bool)
+    tri = np.array([[1.0, 1.0, 1.0], [3.0, 1.0, 1.0], [1.0, 3.0, 2.0]])
+    with pytest.raises(Exception, match="Please provide the mesh vertices"):
+        masker(HalfwayBounceBackBC(indices=[[1], [1], [1]]), bc_mask, missing)
+    with pytest.raises(Exception, match=r"reshaped into an array \(N, 3\)"):
+        masker(HalfwayBounceBackBC(mesh_vertices=tri[:, :2]), bc_mask, missing)
+    with pytest.raises(Exception, match="three consecutive rows per triangle"):
+        masker(HalfwayBounceBackBC(mesh_vertices=tri[:2]), bc_mask, missing)
+    with pytest.raises(Exception, match="exceed domain dimensions"):
+        masker(HalfwayBounceBackBC(mesh_vertices=tri + 6.0), bc_mask, missing)
+    bc = HalfwayBounceBackBC(mesh_vertices=tri)
+    with pytest.raises(Exception, match="no CPU fallback"):
+        masker(bc, bc_mask, missing)
+    assert bc.mesh_vertices is not None  # only a successful call consumes the vertices (reference L212-213)

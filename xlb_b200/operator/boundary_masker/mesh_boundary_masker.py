@@ -48,8 +48,6 @@ class MeshBoundaryMasker(Operator):
         assert mesh_vertices.ndim == 2 and mesh_vertices.shape[1] == vs.d, "Mesh points must be reshaped into an array (N, 3) where N indicates number of points!"
         if mesh_vertices.shape[0] % 3:
             raise ValueError(f"mesh_vertices has {mesh_vertices.shape[0]} rows: three consecutive rows per triangle are expected")
-        native.require_cuda(bc_mask, "bc_mask")
-        native.require_cuda(missing_mask, "missing_mask")
         if bc_mask.dtype != torch.uint8 or missing_mask.dtype != torch.bool:
             raise TypeError("bc_mask must be uint8 and missing_mask bool")
         dims = native.dims_of(missing_mask, vs.d)
@@ -64,6 +62,8 @@ class MeshBoundaryMasker(Operator):
         if start_index is not None:  # local coordinates of this slab; triangles elsewhere fall outside the padded volume and are skipped
             mesh_vertices = mesh_vertices - np.asarray(start_index, dtype=mesh_vertices.dtype)[: vs.d]
         assert not getattr(bc, "needs_mesh_distance", False), 'Please use "MeshDistanceBoundaryMasker" if this BC needs mesh distance!'
+        native.require_cuda(bc_mask, "bc_mask")
+        native.require_cuda(missing_mask, "missing_mask")
         bc.__dict__.pop("mesh_vertices", None)  # reference L212-213: the BC is done with its vertices
 
         verts = torch.as_tensor(np.ascontiguousarray(mesh_vertices, dtype=np.float32), device=bc_mask.device)
