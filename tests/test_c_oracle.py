@@ -4,7 +4,7 @@ produced by the reference's own Python and against the numpy oracle.  CPU only."
 import numpy as np
 import pytest
 
-from common import LATE_CASES, STEP_CASES, load_golden, oracle_bcs, oracle_run, rel_err
+from common import LATE_CASES, STEP_CASES, load_golden, oracle_bcs, rel_err
 from oracle import lbm_c
 from oracle import lbm_numpy as O
 

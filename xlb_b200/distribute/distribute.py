@@ -13,7 +13,6 @@ Here the decomposition is a property of the grid (one process per GPU under torc
 With a single slab both return the operator itself.
 """
 
-import torch
 
 from xlb_b200.distribute.halo import exchange_wrapped_faces
 

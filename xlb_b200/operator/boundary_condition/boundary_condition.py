@@ -14,9 +14,7 @@ import numpy as np
 import torch
 
 from xlb_b200 import native
-from xlb_b200.compute_backend import ComputeBackend
 from xlb_b200.default_config import DefaultConfig
-from xlb_b200.field import Field
 from xlb_b200.operator.boundary_condition.boundary_condition_registry import boundary_condition_registry
 from xlb_b200.operator.operator import Operator
 from xlb_b200.operator._util import to_device_field

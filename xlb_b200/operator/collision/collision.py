@@ -1,7 +1,6 @@
 """Base class of collision operators (reference: xlb/operator/collision/collision.py) + the shared native call."""
 
 from xlb_b200 import native
-from xlb_b200.compute_backend import ComputeBackend
 from xlb_b200.operator.operator import Operator
 from xlb_b200.operator._util import empty_like_field, to_device_field
 

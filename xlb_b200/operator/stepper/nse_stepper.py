@@ -22,7 +22,6 @@ from xlb_b200.compute_backend import ComputeBackend
 from xlb_b200.default_config import DefaultConfig
 from xlb_b200.helper.check_boundary_overlaps import check_bc_overlaps
 from xlb_b200.helper.nse_solver import create_nse_fields
-from xlb_b200.operator.boundary_condition.boundary_condition import ImplementationStep
 from xlb_b200.operator.boundary_masker import IndicesBoundaryMasker, MeshBoundaryMasker
 from xlb_b200.operator.collision import BGK, KBC, ForcedCollision, SmagorinskyLESBGK
 from xlb_b200.operator.equilibrium import QuadraticEquilibrium
