@@ -178,3 +178,41 @@ def test_zouhe_prescribed_values_both_conventions():
     init("D3Q19", ComputeBackend.WARP)
     bc_c = RegularizedBC("velocity", prescribed_value=(0.03, 0.0, 0.0))
     assert np.allclose(bc_c._prescribed_values_at(cells, missing, shape), 0.03)
+
+
+def test_new_entry_points_validate_their_arguments_without_a_device():
+    """Argument-error paths of the entry points added for SURVEY §8f N3 / N4: they return before touching CUDA, so the ctypes
+    signatures (argument count and order) are exercised here on the CPU."""
+    import ctypes as C
+
+    from xlb_b200 import native
+
+    lib = native.lib()
+    err = lambda: lib.xlbn_last_error().decode()
+    dims = native.int3((4, 4, 4))
+    one = C.c_void_p(1)  # non-NULL, never dereferenced on these paths
+    # xlbn_collide_ext: NULL arrays, unknown / unsupported collisions, forced without u / force
+    assert lib.xlbn_collide_ext(native.D3Q19, native.BGK, native.F32, None, 1, None, 1, None, 1, None, 0, None, 0, 1.0, None, 0.17, dims, None) < 0 and "NULL array" in err()
+    assert lib.xlbn_collide_ext(native.D3Q19, 3, native.F32, one, 1, one, 1, one, 1, None, 0, None, 0, 1.0, None, 0.17, dims, None) < 0 and "unknown collision" in err()
+    assert lib.xlbn_collide_ext(native.D3Q19, native.KBC, native.F32, one, 1, one, 1, one, 1, one, 1, None, 0, 1.0, None, 0.17, dims, None) < 0 and "D3Q19" in err()
+    dims2 = native.int3((4, 4, 1))
+    assert lib.xlbn_collide_ext(native.D2Q9, native.SMAGORINSKY_LES_BGK, native.F32, one, 1, one, 1, one, 1, None, 0, None, 0, 1.0, None, 0.17, dims2, None) < 0 and "3-D velocity sets only" in err()
+    assert lib.xlbn_collide_ext(native.D3Q27, native.BGK | native.COLLISION_FORCED, native.F32, one, 1, one, 1, one, 1, one, 1, None, 0, 1.0, None, 0.17, dims, None) < 0 and "needs u and the force" in err()
+    # xlbn_exact_difference: NULL argument
+    assert lib.xlbn_exact_difference(native.D3Q19, native.F32, one, 1, one, 1, one, 1, one, 1, one, 1, None, dims, None) < 0 and "NULL argument" in err()
+    # xlbn_mask_mesh: 2-D lattice, NULL, bad id, bad edge test
+    assert lib.xlbn_mask_mesh(native.D2Q9, one, 1, 1, 0, dims2, one, one, one, None) < 0 and "3-D lattices only" in err()
+    assert lib.xlbn_mask_mesh(native.D3Q19, None, 1, 1, 0, dims, one, one, one, None) < 0 and "NULL argument" in err()
+    assert lib.xlbn_mask_mesh(native.D3Q19, one, 1, 255, 0, dims, one, one, one, None) < 0 and "id 255" in err()
+    assert lib.xlbn_mask_mesh(native.D3Q19, one, 1, 1, 7, dims, one, one, one, None) < 0 and "edge_test 7" in err()
+    # stepper setters on a NULL handle
+    assert lib.xlbn_stepper_set_force(None, (C.c_double * 3)(1e-5, 0.0, 0.0)) < 0 and "NULL stepper" in err()
+    assert lib.xlbn_stepper_set_smagorinsky(None, 0.17) < 0 and "NULL stepper" in err()
+    # stepper_create argument checks for the new options (they fail before cudaMalloc)
+    out = C.c_void_p()
+    desc = native.StepperDesc(lattice=native.D2Q9, collision=native.SMAGORINSKY_LES_BGK, compute_dtype=native.F32, store_dtype=native.F32, n_bc=0, cells_per_thread=0, bcs=None)
+    assert lib.xlbn_stepper_create(C.byref(desc), C.byref(out)) < 0 and "3-D velocity sets only" in err()
+    desc = native.StepperDesc(lattice=native.D3Q19, collision=native.BGK, compute_dtype=native.F32, store_dtype=native.F32, n_bc=0, cells_per_thread=301, bcs=None)
+    assert lib.xlbn_stepper_create(C.byref(desc), C.byref(out)) < 0 and "lean KBC" in err()
+    desc = native.StepperDesc(lattice=native.D3Q19, collision=5, compute_dtype=native.F32, store_dtype=native.F32, n_bc=0, cells_per_thread=0, bcs=None)
+    assert lib.xlbn_stepper_create(C.byref(desc), C.byref(out)) < 0 and "unknown collision" in err()
