@@ -94,6 +94,8 @@ typedef struct xlbn_stepper_desc {
   int32_t cells_per_thread; /* tuning knob: 0 = library default; 1, 2, 4, 8 = scalar path, that many z-cells per thread;
                                102, 104 = packed fp32x2 pair path (FFMA2; fp32 compute, fp32/fp16 storage only);
                                202 = half2-state pair path (FP32FP16 BGK only; the default for that policy);
+                               203 = 202 with a leaner boundary variant for warps whose boundary cells are all
+                                     FullwayBounceBack (same results; a tuning candidate);
                                301 = KBC only: register-lean formulation of the collision, one cell per thread (same algebra,
                                      rounding-level differences; a tuning candidate, not the default) */
   const xlbn_bc_desc* bcs;  /* n_bc entries, copied */

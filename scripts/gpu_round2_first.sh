@@ -22,6 +22,12 @@ run --lattice D3Q27 --collision KBC --policy FP32FP16 --cells-per-thread 301
 # wind tunnel with a mesh body (N3): voxelisation + 200 steps
 timeout 300 python examples/windtunnel_mesh.py 256 96 96 200 2>&1 | tail -14 | tee gpurun_out/r2_windtunnel_mesh.log
 timeout 300 python examples/turbulent_channel.py 32 400 2>&1 | tail -8 | tee gpurun_out/r2_turbulent_channel.log
+# FP32FP16: half2-state path (default, 202) vs the split boundary variant (203)
+run --policy FP32FP16
+run --policy FP32FP16 --cells-per-thread 203
+run --policy FP32FP16 --config periodic
+run --lattice D3Q27 --policy FP32FP16
+run --lattice D3Q27 --policy FP32FP16 --cells-per-thread 203
 # extended collision kernels (N4): first numbers
 run --collision SmagorinskyLESBGK
 run --collision SmagorinskyLESBGK --config periodic

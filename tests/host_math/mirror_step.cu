@@ -42,7 +42,7 @@ int host_step_pair(const StepCall& c) {
   StepParams<TS> p;
   if (int e = fill_step_params<L, TS>(c, p)) return e;
   if (c.nz % 2) return fail(XLBN_E_SHAPE, "mirror: pair paths need an even nz");
-  if constexpr (MODE == 2) {  // what bc_precompute_kernel does on the device: EquilibriumBC cells' constant update
+  if constexpr (MODE != 1) {  // what bc_precompute_kernel does on the device: EquilibriumBC cells' constant update
     BcEntry* table = c.table_rw;
     for (int id = 0; id < 256; ++id) {
       if (table[id].kind != XLBN_BC_EQUILIBRIUM) continue;
@@ -62,11 +62,16 @@ int host_step_pair(const StepCall& c) {
           else if (first && !last) step_body_pk<L, COLL, TS, 2, 1>(p, x, y, z0);
           else if (last && !first) step_body_pk<L, COLL, TS, 2, 2>(p, x, y, z0);
           else step_body_pk<L, COLL, TS, 2, 3>(p, x, y, z0);
-        } else {
+        } else if constexpr (MODE == 2) {
           if (!first && !last) step_body_h2<L, 0>(p, x, y, z0);
           else if (first && !last) step_body_h2<L, 1>(p, x, y, z0);
           else if (last && !first) step_body_h2<L, 2>(p, x, y, z0);
           else step_body_h2<L, 3>(p, x, y, z0);
+        } else {  // MODE 5: boundary warps split by kind
+          if (!first && !last) step_body_h2<L, 0, true>(p, x, y, z0);
+          else if (first && !last) step_body_h2<L, 1, true>(p, x, y, z0);
+          else if (last && !first) step_body_h2<L, 2, true>(p, x, y, z0);
+          else step_body_h2<L, 3, true>(p, x, y, z0);
         }
       }
   }
@@ -79,7 +84,7 @@ int host_step_v(const StepCall& c) {
   if constexpr (!kExtCollision<COLL> && sizeof(TC) == 4) {
     if (c.requested_v == 102) return host_step_pair<L, COLL, TS, 1>(c);
     if constexpr (sizeof(TS) == 2 && COLL == XLBN_BGK)
-      if (c.requested_v == 202) return host_step_pair<L, COLL, TS, 2>(c);
+      if (c.requested_v == 202 || c.requested_v == 203) return c.requested_v == 202 ? host_step_pair<L, COLL, TS, 2>(c) : host_step_pair<L, COLL, TS, 5>(c);
   }
   if constexpr (!kExtCollision<COLL>) {  // the library builds the extended operators with one cell per thread only
     if (c.requested_v == 2) return host_step<L, COLL, TC, TS, 2>(c);

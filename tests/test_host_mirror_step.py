@@ -94,7 +94,7 @@ def mirror_run(lib, g, steps=None, v=1, lean_kbc=False, masks=None):
     return fa
 
 
-@pytest.mark.parametrize("v", [102, 202])
+@pytest.mark.parametrize("v", [102, 202, 203])
 @pytest.mark.parametrize("name", ["cavity_d3q19_bgk_fp32", "cavity_d3q19_bgk_fp32fp16", "sphere_d3q19_bgk_fp32fp16", "sphere_d3q27_kbc_fp32", "cavity_d2q9_kbc_fp32",
                                   "warp_tunnel_d3q19_bgk_zouhe_pressure", "periodic_d3q19_bgk_fp32"])  # fmt: skip
 def test_pair_paths_match_the_reference_vectors(mirror, name, v):
@@ -102,13 +102,15 @@ def test_pair_paths_match_the_reference_vectors(mirror, name, v):
     two cells per thread, FADD2 / FMUL2 / FFMA2 arithmetic, reciprocal-based divisions; per-half boundary handling with the
     precomputed EquilibriumBC update in the half2 path."""
     g = load_golden(name)
-    if v == 202 and not (g["policy"] == "FP32FP16" and g["collision"] == "BGK"):
+    if v in (202, 203) and not (g["policy"] == "FP32FP16" and g["collision"] == "BGK"):
         pytest.skip("the half2-state path exists for FP32FP16 BGK only")
     if g["shape"][-1] % 2:
         pytest.skip("odd nz: the library falls back to one cell per thread")
     f = mirror_run(mirror, g, v=v)
     assert rel_err(f, g["f_final"]) <= RTOL[g["policy"]]
     assert rel_err(f, mirror_run(mirror, g)) <= (3e-6 if g["policy"] == "FP32FP32" else 1e-3)
+    if v == 203:  # the split boundary variant must give the bits of the half2-state path it specialises
+        assert np.array_equal(f, mirror_run(mirror, g, v=202))
 
 
 def mirror_run_slabs(lib, g, n_slabs, steps):

@@ -216,6 +216,7 @@ LATE_2D = [(n, b, 0) for n in LATE_CASES for b in ("WARP", "JAX")]
 WARP_VECTORS = [(n, "WARP", 0) for n in WARP_CASES]
 N4_VECTORS = [(n, "WARP", 0) for n in WARP_CASES_N4]
 LEAN_KBC = [(n, "WARP", 301) for n in KBC_CASES]
+SPLIT_H2 = [(n, "WARP", 203) for n in ("cavity_d3q19_bgk_fp32fp16", "sphere_d3q19_bgk_fp32fp16")]
 
 
 @pytest.mark.parametrize("name,backend,v", LATE_2D)
@@ -239,6 +240,12 @@ def test_first_run_of_the_extended_collision_kernels(name, backend, v):
 def test_first_run_of_the_lean_kbc_variant(name, backend, v):
     """cells_per_thread = 301 (register-lean KBC): host-validated, never run on a GPU."""
     check(step_group(LEAN_KBC), f"{name}|{backend}|{v}")
+
+
+@pytest.mark.parametrize("name,backend,v", SPLIT_H2)
+def test_first_run_of_the_split_boundary_half2_variant(name, backend, v):
+    """cells_per_thread = 203: half2-state path with a Fullway-only boundary variant (host-validated, bit-identical to 202)."""
+    check(step_group(SPLIT_H2), f"{name}|{backend}|{v}")
 
 
 @pytest.mark.parametrize("lattice", ["D3Q19", "D3Q27", "D2Q9"])

@@ -79,7 +79,7 @@ int xlbn_stepper_create(const xlbn_stepper_desc* desc, xlbn_stepper** out) {
   if (desc->compute_dtype == XLBN_F32 && desc->store_dtype == XLBN_F64) return fail(XLBN_E_DTYPE, "stepper_create: no FP32FP64 policy");
   if (desc->n_bc < 0 || (desc->n_bc > 0 && !desc->bcs)) return fail(XLBN_E_ARG, "stepper_create: bad BC list");
   const int cpt = desc->cells_per_thread;
-  if (cpt != 0 && cpt != 1 && cpt != 2 && cpt != 4 && cpt != 8 && cpt != 102 && cpt != 104 && cpt != 202 && cpt != 301)
+  if (cpt != 0 && cpt != 1 && cpt != 2 && cpt != 4 && cpt != 8 && cpt != 102 && cpt != 104 && cpt != 202 && cpt != 203 && cpt != 301)
     return fail(XLBN_E_ARG, "stepper_create: cells_per_thread = %d", cpt);
   if (cpt == 301 && desc->collision != XLBN_KBC) return fail(XLBN_E_ARG, "stepper_create: cells_per_thread = 301 selects the lean KBC collision; the stepper's collision is %d", desc->collision);
 

@@ -314,7 +314,7 @@ struct StepTraits {
   // V*Q population registers (x2 for fp64) + collision temporaries + addresses.
   static constexpr int kW = (int)(sizeof(TC) / 4);
   static constexpr int kRegs = (COLL & kLeanKbc) ? (L::Q + 45) * kW  // lean KBC: f[] + (rho, u, usqr, pi / sv, sums) and addresses
-                               : MODE == 2 ? L::Q + 45  // populations stay packed as half2: q registers for two cells
+                               : (MODE == 2 || MODE == 5) ? L::Q + 45  // populations stay packed as half2: q registers for two cells
                                : PK      ? V * L::Q + (kBaseCollision<COLL> == XLBN_KBC ? 4 : 2) * L::Q + 29  // pair temporaries take two registers each
                                          : V * L::Q * kW + (kBaseCollision<COLL> == XLBN_KBC ? L::Q * kW + 24 : 24) + (kForcedCollision<COLL> ? 8 * kW : 0) +
                                                (kBaseCollision<COLL> == XLBN_SMAGORINSKY_LES_BGK ? 8 * kW : 0) + 5;
@@ -572,17 +572,18 @@ __global__ void bc_precompute_kernel(BcEntry* table, float omega) {
   XLBN_FOR(L::Q, l) table[id].eq_out[l] = f[l]; XLBN_END
 }
 
-// moments + equilibrium + BGK + narrow + store for the two cells of a half2-state thread.  WITH_BC: per-half handling of
+// moments + equilibrium + BGK + narrow + store for the two cells of a half2-state thread.  BCV = 2: per-half handling of
 // FullwayBounceBack (bit copy of the opposite population's half; fp16 -> fp32 -> fp16 is exact) and EquilibriumBC cells
-// (the precomputed constant update, BcEntry::eq_out); id_lo / id_hi = bc ids of the two cells.
-template <class L, int XC, bool WITH_BC>
+// (the precomputed constant update, BcEntry::eq_out); BCV = 1: FullwayBounceBack only (no table pointers, no constant
+// loads: the walls of a closed box); BCV = 0: no boundary cell.  id_lo / id_hi = bc ids of the two cells.
+template <class L, int XC, int BCV>
 XLBN_DEV void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L::Q], const unsigned cell, const int id_lo, const int id_hi) {
   using TS = __half;
   constexpr int Q = L::Q;
   bool eq_lo = false, eq_hi = false, fw_lo = false, fw_hi = false;
   const float* out_lo = nullptr;
   const float* out_hi = nullptr;
-  if constexpr (WITH_BC) {
+  if constexpr (BCV == 2) {
     const int k_lo = id_lo ? (int)p.kinds[id_lo] : 0, k_hi = id_hi ? (int)p.kinds[id_hi] : 0;
     eq_lo = k_lo == XLBN_BC_EQUILIBRIUM;
     eq_hi = k_hi == XLBN_BC_EQUILIBRIUM;
@@ -590,6 +591,9 @@ XLBN_DEV void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L
     fw_hi = k_hi == XLBN_BC_FULLWAY_BOUNCE_BACK;
     out_lo = p.table[id_lo].eq_out;
     out_hi = p.table[id_hi].eq_out;
+  } else if constexpr (BCV == 1) {  // the warp holds fluid and FullwayBounceBack cells only
+    fw_lo = id_lo && p.kinds[id_lo] == XLBN_BC_FULLWAY_BOUNCE_BACK;
+    fw_hi = id_hi && p.kinds[id_hi] == XLBN_BC_FULLWAY_BOUNCE_BACK;
   }
   // moments (macroscopic.py:43-47)
   f32x2 rho(0.0f), u[L::D];
@@ -619,12 +623,12 @@ XLBN_DEV void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L
     cu *= f32x2(3.0f);
     const f32x2 feq = rho * f32x2(L::w(l)) * (fma_(cu, fma_(f32x2(0.5f), cu, f32x2(1.0f)), f32x2(1.0f)) - usqr);
     f32x2 out = fma_(-omega, f - feq, f);
-    if constexpr (WITH_BC) {  // bc_equilibrium.py:76-86 followed by the ordinary collision = a per-BC constant
+    if constexpr (BCV == 2) {  // bc_equilibrium.py:76-86 followed by the ordinary collision = a per-BC constant
       if (eq_lo) out.v.x = out_lo[l];
       if (eq_hi) out.v.y = out_hi[l];
     }
     __half2 o = __float22half2_rn(out.v);
-    if constexpr (WITH_BC) {  // bc_fullway_bounce_back.py:60-72: out[l] = f_post_stream[opp l]
+    if constexpr (BCV != 0) {  // bc_fullway_bounce_back.py:60-72: out[l] = f_post_stream[opp l]
       if (fw_lo) o = __halves2half2(__low2half(h[L::opp(l)]), __high2half(o));
       if (fw_hi) o = __halves2half2(__low2half(o), __high2half(h[L::opp(l)]));
     }
@@ -646,7 +650,9 @@ XLBN_DEV void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L
 // relaxation, whose result is narrowed (one F2FP) and stored immediately.  Live state: q + ~25 registers for two cells,
 // so the kernel keeps the residency of the one-cell path while issuing ~2.5x fewer instructions per cell (FADD2 / FMUL2 /
 // FFMA2 for both cells at once); the fp16 path is issue-bound otherwise (profiles/README.md).
-template <class L, int XC>
+// SPLIT (tuning variant, cells_per_thread = 203): warps whose boundary cells are all FullwayBounceBack take a leaner boundary
+// variant without the EquilibriumBC table pointers / constant loads.
+template <class L, int XC, bool SPLIT = false>
 XLBN_DEV void step_body_h2(const StepParams<__half>& p, const int x, const int y, const int z0) {
   using TS = __half;
   constexpr int Q = L::Q, V = 2;
@@ -696,19 +702,27 @@ XLBN_DEV void step_body_h2(const StepParams<__half>& p, const int x, const int y
   if (!warp_any_bc) {
     __half2 h[Q];
     load_all(h);
-    h2_collide_store<L, XC, false>(p, h, cell, 0, 0);
+    h2_collide_store<L, XC, 0>(p, h, cell, 0, 0);
     return;
   }
   if (XLBN_ALL(active, simple(ids.v[0], k0) && simple(ids.v[1], k1))) {
+    if constexpr (SPLIT) {
+      if (XLBN_ALL(active, k0 != XLBN_BC_EQUILIBRIUM && k1 != XLBN_BC_EQUILIBRIUM)) {
+        __half2 h[Q];
+        load_all(h);
+        h2_collide_store<L, XC, 1>(p, h, cell, ids.v[0], ids.v[1]);
+        return;
+      }
+    }
     __half2 h[Q];
     load_all(h);
-    h2_collide_store<L, XC, true>(p, h, cell, ids.v[0], ids.v[1]);
+    h2_collide_store<L, XC, 2>(p, h, cell, ids.v[0], ids.v[1]);
     return;
   }
   if (!any_bc) {
     __half2 h[Q];
     load_all(h);
-    h2_collide_store<L, XC, false>(p, h, cell, 0, 0);
+    h2_collide_store<L, XC, 0>(p, h, cell, 0, 0);
     return;
   }
   __half2 h[Q];
@@ -738,6 +752,11 @@ __global__ void __launch_bounds__(StepTraits<L, COLL, TC, TS, V, MODE>::kThreads
     else if (first && !last) step_body_h2<L, 1>(p, x, y, z0);
     else if (last && !first) step_body_h2<L, 2>(p, x, y, z0);
     else step_body_h2<L, 3>(p, x, y, z0);
+  } else if constexpr (MODE == 5) {
+    if (!first && !last) step_body_h2<L, 0, true>(p, x, y, z0);
+    else if (first && !last) step_body_h2<L, 1, true>(p, x, y, z0);
+    else if (last && !first) step_body_h2<L, 2, true>(p, x, y, z0);
+    else step_body_h2<L, 3, true>(p, x, y, z0);
   } else if constexpr (MODE == 1) {
     if (!first && !last) step_body_pk<L, COLL, TS, V, 0>(p, x, y, z0);
     else if (first && !last) step_body_pk<L, COLL, TS, V, 1>(p, x, y, z0);
@@ -794,7 +813,7 @@ int launch_step_base(const StepParams<TS>& p, int x_count, int requested_v, cons
   int req = requested_v;
   constexpr bool can_h2 = sizeof(TC) == 4 && sizeof(TS) == 2 && COLL == XLBN_BGK;
   if (req == 0) req = can_h2 ? 202 : 1;
-  if (req == 202) {
+  if (req == 202 || req == 203) {
     if constexpr (can_h2) {
       if (pick_cells_per_thread(2, 1, (int)sizeof(TS), p.nz, p.bc, {f0, f1, g0, g1, o0, o1}) == 2) {
         if (eq_omega_state && !(p.omega == *eq_omega_state)) {
@@ -804,6 +823,7 @@ int launch_step_base(const StepParams<TS>& p, int x_count, int requested_v, cons
           XLBN_CUDA_OK(cudaStreamSynchronize(stream));
           *eq_omega_state = p.omega;
         }
+        if (req == 203) return launch_step_v<L, COLL, TC, TS, 2, 5>(p, x_count, stream);
         return launch_step_v<L, COLL, TC, TS, 2, 2>(p, x_count, stream);
       }
       req = 1;  // odd nz or misaligned arrays: scalar fallback
