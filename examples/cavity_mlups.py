@@ -1,7 +1,7 @@
-"""Lid-driven cavity throughput (MLUPS), written against the XLB operator API exactly as a user of Autodesk/XLB would
-(same calls as the reference's examples/performance/mlups_3d.py: xlb.init, grid_factory, bounding_box_indices,
-EquilibriumBC / FullwayBounceBackBC, IncompressibleNavierStokesStepper, prepare_fields, the step-and-swap loop,
-wp.synchronize).  `import xlb` resolves to xlb_b200 through the alias package at the repository root.
+"""Lid-driven cavity throughput (MLUPS), written against the XLB operator API as a user of Autodesk/XLB would (the workflow of
+the reference's examples/performance/mlups_3d.py: xlb.init, grid_factory, bounding_box_indices, EquilibriumBC /
+FullwayBounceBackBC, IncompressibleNavierStokesStepper, prepare_fields, the step-and-swap loop, wp.synchronize).
+`import xlb` resolves to xlb_b200 through the alias package at the repository root.
 
     python examples/cavity_mlups.py 512 200 warp fp32/fp32
 """
@@ -23,40 +23,50 @@ from xlb.operator.stepper import IncompressibleNavierStokesStepper
 from xlb.operator.boundary_condition import FullwayBounceBackBC, EquilibriumBC
 from xlb.distribute import distribute
 
-parser = argparse.ArgumentParser()
-parser.add_argument("cube_edge", type=int)
-parser.add_argument("num_steps", type=int)
-parser.add_argument("compute_backend", type=str, help="jax or warp: selects the call convention, both run the CUDA kernels")
-parser.add_argument("precision", type=str, help="fp32/fp32, fp64/fp64, fp64/fp32, fp32/fp16")
-args = parser.parse_args()
+POLICIES = {"fp32/fp32": PrecisionPolicy.FP32FP32, "fp64/fp64": PrecisionPolicy.FP64FP64, "fp64/fp32": PrecisionPolicy.FP64FP32, "fp32/fp16": PrecisionPolicy.FP32FP16}
+LID_VELOCITY, OMEGA, WARMUP_STEPS = (0.02, 0.0, 0.0), 1.0, 5
 
-backend = ComputeBackend.JAX if args.compute_backend == "jax" else ComputeBackend.WARP
-policy = {"fp32/fp32": PrecisionPolicy.FP32FP32, "fp64/fp64": PrecisionPolicy.FP64FP64, "fp64/fp32": PrecisionPolicy.FP64FP32, "fp32/fp16": PrecisionPolicy.FP32FP16}[args.precision]
-xlb.init(velocity_set=xlb.velocity_set.D3Q19(precision_policy=policy, compute_backend=backend), default_backend=backend, default_precision_policy=policy)
 
-n = args.cube_edge
-grid = grid_factory((n, n, n))
-box = grid.bounding_box_indices()
-box_no_edge = grid.bounding_box_indices(remove_edges=True)
-lid = box_no_edge["top"]
-walls = [box["bottom"][i] + box["left"][i] + box["right"][i] + box["front"][i] + box["back"][i] for i in range(3)]
-walls = np.unique(np.array(walls), axis=-1).tolist()
-boundary_conditions = [EquilibriumBC(rho=1.0, u=(0.02, 0.0, 0.0), indices=lid), FullwayBounceBackBC(indices=walls)]
-stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=boundary_conditions, collision_type="BGK")
-if backend == ComputeBackend.JAX:
-    stepper = distribute(stepper, grid, xlb.velocity_set.D3Q19(precision_policy=policy, compute_backend=backend))
+def command_line():
+    cli = argparse.ArgumentParser(description=__doc__.splitlines()[0])
+    cli.add_argument("cube_edge", type=int)
+    cli.add_argument("num_steps", type=int)
+    cli.add_argument("compute_backend", choices=["jax", "warp"], help="selects the call convention; both run the CUDA kernels")
+    cli.add_argument("precision", choices=sorted(POLICIES))
+    return cli.parse_args()
 
-omega = 1.0
-f_0, f_1, bc_mask, missing_mask = stepper.prepare_fields()
-for i in range(5):  # warm-up (the reference script times its JIT compilation too; nothing is compiled here)
-    f_0, f_1 = stepper(f_0, f_1, bc_mask, missing_mask, omega, i)
-    f_0, f_1 = f_1, f_0
-wp.synchronize()
-start = time.time()
-for i in range(args.num_steps):
-    f_0, f_1 = stepper(f_0, f_1, bc_mask, missing_mask, omega, i)
-    f_0, f_1 = f_1, f_0
-wp.synchronize()
-elapsed = time.time() - start
-print(f"Simulation completed in {elapsed:.2f} seconds")
-print(f"MLUPs: {n**3 * args.num_steps / elapsed / 1e6:.2f}")
+
+def cavity(edge, backend, policy):
+    """Closed box: moving lid (top face without its rim) as EquilibriumBC, the other five faces as full-way bounce-back."""
+    lattice = xlb.velocity_set.D3Q19(precision_policy=policy, compute_backend=backend)
+    xlb.init(velocity_set=lattice, default_backend=backend, default_precision_policy=policy)
+    grid = grid_factory((edge,) * 3)
+    faces, faces_without_rim = grid.bounding_box_indices(), grid.bounding_box_indices(remove_edges=True)
+    wall_cells = [sum((faces[side][axis] for side in ("bottom", "left", "right", "front", "back")), []) for axis in range(3)]
+    wall_cells = np.unique(np.array(wall_cells), axis=-1).tolist()
+    bcs = [EquilibriumBC(rho=1.0, u=LID_VELOCITY, indices=faces_without_rim["top"]), FullwayBounceBackBC(indices=wall_cells)]
+    stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=bcs, collision_type="BGK")
+    if backend == ComputeBackend.JAX:  # the reference shards its JAX stepper explicitly; here the grid already knows its slab
+        stepper = distribute(stepper, grid, lattice)
+    return stepper
+
+
+def advance(stepper, fields, steps, first_step=0):
+    f_now, f_next, bc_mask, missing_mask = fields
+    for t in range(first_step, first_step + steps):
+        f_now, f_next = stepper(f_now, f_next, bc_mask, missing_mask, OMEGA, t)
+        f_now, f_next = f_next, f_now
+    wp.synchronize()
+    return f_now, f_next, bc_mask, missing_mask
+
+
+if __name__ == "__main__":
+    args = command_line()
+    backend = ComputeBackend.JAX if args.compute_backend == "jax" else ComputeBackend.WARP
+    stepper = cavity(args.cube_edge, backend, POLICIES[args.precision])
+    fields = advance(stepper, stepper.prepare_fields(), WARMUP_STEPS)  # the reference script times its JIT compilation too; nothing compiles here
+    start = time.time()
+    advance(stepper, fields, args.num_steps, first_step=WARMUP_STEPS)
+    elapsed = time.time() - start
+    print(f"Simulation completed in {elapsed:.2f} seconds")
+    print(f"MLUPs: {args.cube_edge**3 * args.num_steps / elapsed / 1e6:.2f}")

@@ -4,28 +4,21 @@ gives the reference's import surface: enums, `init`, velocity sets, grid, operat
 All arithmetic runs in hand-written CUDA kernels reached through the C ABI in include/xlb_b200.h; there is no CPU path.
 """
 
+import importlib
+
 __version__ = "0.1.0"
 
-# Enum classes
-from xlb_b200.compute_backend import ComputeBackend as ComputeBackend
-from xlb_b200.precision_policy import PrecisionPolicy as PrecisionPolicy, Precision as Precision
-from xlb_b200.physics_type import PhysicsType as PhysicsType
-from xlb_b200.grid_backend import GridBackend as GridBackend
+from xlb_b200.compute_backend import ComputeBackend  # noqa: F401
+from xlb_b200.default_config import DefaultConfig, init  # noqa: F401
+from xlb_b200.grid_backend import GridBackend  # noqa: F401
+from xlb_b200.physics_type import PhysicsType  # noqa: F401
+from xlb_b200.precision_policy import Precision, PrecisionPolicy  # noqa: F401
 
-# Config
-from xlb_b200.default_config import init as init, DefaultConfig as DefaultConfig
-
-# Velocity sets, operators, grid, helpers, utils, distribution
-import xlb_b200.velocity_set
-import xlb_b200.operator.equilibrium
-import xlb_b200.operator.collision
-import xlb_b200.operator.stream
-import xlb_b200.operator.boundary_condition
-import xlb_b200.operator.boundary_masker
-import xlb_b200.operator.macroscopic
-import xlb_b200.operator.stepper
-import xlb_b200.operator.force
-import xlb_b200.grid
-import xlb_b200.helper
-import xlb_b200.utils
-import xlb_b200.distribute
+# sub-packages that `import xlb` makes available as attributes (xlb.velocity_set.D3Q19, xlb.operator.stepper, ...)
+for _name in (
+    "velocity_set", "grid", "helper", "utils", "distribute",
+    "operator.equilibrium", "operator.collision", "operator.stream", "operator.macroscopic", "operator.force",
+    "operator.boundary_condition", "operator.boundary_masker", "operator.stepper",
+):  # fmt: skip
+    importlib.import_module(f"{__name__}.{_name}")
+del _name

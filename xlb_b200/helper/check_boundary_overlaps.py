@@ -8,23 +8,25 @@ from xlb_b200.compute_backend import ComputeBackend
 
 def _has_duplicates(index_rows) -> bool:
     arr = np.asarray(index_rows)
-    if arr.size == 0:
-        return False
-    return np.unique(arr, axis=-1).shape[-1] != arr.shape[-1]
+    return arr.size > 0 and np.unique(arr, axis=-1).shape[-1] != arr.shape[-1]
+
+
+def _report(compute_backend, error, warning):
+    if compute_backend == ComputeBackend.WARP:
+        raise ValueError(error)
+    print("WARNING: " + warning)
 
 
 def check_bc_overlaps(bclist, dim, compute_backend):
-    merged = [[] for _ in range(dim)]
-    for bc in bclist:
-        if bc.indices is None:
-            continue
+    with_indices = [bc for bc in bclist if bc.indices is not None]
+    for bc in with_indices:
+        name = bc.__class__.__name__
         if _has_duplicates(bc.indices):
-            if compute_backend == ComputeBackend.WARP:
-                raise ValueError(f"Boundary condition {bc.__class__.__name__} has duplicate indices!")
-            print(f"WARNING: there are duplicate indices in {bc.__class__.__name__} and hence the order in bc list matters!")
-        for d in range(dim):
-            merged[d] += list(bc.indices[d])
+            _report(compute_backend, f"Boundary condition {name} has duplicate indices!", f"there are duplicate indices in {name} and hence the order in bc list matters!")
+    merged = [[i for bc in with_indices for i in bc.indices[d]] for d in range(dim)]
     if _has_duplicates(merged):
-        if compute_backend == ComputeBackend.WARP:
-            raise ValueError("Boundary condition list containes duplicate indices!")
-        print("WARNING: there are duplicate indices in the boundary condition list and hence the order in this list matters!")
+        _report(
+            compute_backend,
+            "Boundary condition list containes duplicate indices!",
+            "there are duplicate indices in the boundary condition list and hence the order in this list matters!",
+        )

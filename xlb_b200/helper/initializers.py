@@ -5,14 +5,12 @@ from xlb_b200.operator.equilibrium import QuadraticEquilibrium
 
 
 def initialize_eq(f, grid, velocity_set, precision_policy, compute_backend, rho=None, u=None):
-    if rho is None:
-        rho = grid.create_field(cardinality=1, fill_value=1.0, dtype=precision_policy.compute_precision)
-    if u is None:
-        u = grid.create_field(cardinality=velocity_set.d, fill_value=0.0, dtype=precision_policy.compute_precision)
-    equilibrium = QuadraticEquilibrium(velocity_set, precision_policy, compute_backend)
+    """JAX convention: returns a new field in the store dtype; WARP convention: fills and returns `f`."""
+    compute = precision_policy.compute_precision
+    moments = []
+    for given, cardinality, fill in ((rho, 1, 1.0), (u, velocity_set.d, 0.0)):
+        moments.append(given if given is not None else grid.create_field(cardinality=cardinality, fill_value=fill, dtype=compute))
+    feq = QuadraticEquilibrium(velocity_set, precision_policy, compute_backend)
     if compute_backend == ComputeBackend.JAX:
-        f = equilibrium(rho, u).to(precision_policy.store_precision.torch_dtype)
-    else:
-        f = equilibrium(rho, u, f)
-    del rho, u
-    return f
+        return feq(*moments).to(precision_policy.store_precision.torch_dtype)
+    return feq(*moments, f)

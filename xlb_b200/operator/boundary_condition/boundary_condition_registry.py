@@ -4,21 +4,23 @@ ids are handed out in order of BC *construction*, starting at 1; 0 = no boundary
 They end up in the uint8 ``bc_mask`` and must therefore match the reference's allocation exactly.
 """
 
+FIRST_ID, LAST_ID = 1, 254  # uint8 with 0 (fluid) and 255 (solid) reserved
+
 
 class BoundaryConditionRegistry:
+    """`next_id`, `id_to_bc` and `bc_to_id` are public, as in the reference (scripts reset `next_id` between cases)."""
+
     def __init__(self):
-        self.id_to_bc = {}
-        self.bc_to_id = {}
-        self.next_id = 1  # 0 is reserved for no boundary condition
+        self.next_id = FIRST_ID
+        self.id_to_bc, self.bc_to_id = {}, {}
 
     def register_boundary_condition(self, boundary_condition):
-        _id = self.next_id
-        if _id > 254:
+        assigned = self.next_id
+        if assigned > LAST_ID:
             raise ValueError("more than 254 boundary conditions registered: ids must fit uint8 with 0 / 255 reserved")
-        self.next_id += 1
-        self.id_to_bc[_id] = boundary_condition
-        self.bc_to_id[boundary_condition] = _id
-        return _id
+        self.id_to_bc[assigned], self.bc_to_id[boundary_condition] = boundary_condition, assigned
+        self.next_id = assigned + 1
+        return assigned
 
 
 boundary_condition_registry = BoundaryConditionRegistry()

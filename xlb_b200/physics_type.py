@@ -1,8 +1,5 @@
-"""Physics-type enum (reference: xlb/physics_type.py:6-8)."""
+"""Physics-type enum (reference: xlb/physics_type.py:6-8): NSE = Navier-Stokes, ADE = advection-diffusion."""
 
-from enum import Enum, auto
+from enum import Enum
 
-
-class PhysicsType(Enum):
-    NSE = auto()  # Navier-Stokes
-    ADE = auto()  # Advection-diffusion
+PhysicsType = Enum("PhysicsType", ["NSE", "ADE"])
