@@ -96,8 +96,10 @@ typedef struct xlbn_stepper_desc {
                                202 = half2-state pair path (FP32FP16 BGK only; the default for that policy);
                                203 = 202 with a leaner boundary variant for warps whose boundary cells are all
                                      FullwayBounceBack (same results; a tuning candidate);
-                               301 = KBC only: register-lean formulation of the collision, one cell per thread (same algebra,
-                                     rounding-level differences; a tuning candidate, not the default) */
+                               301 = KBC only: register-lean formulation of the collision, one cell per thread (same algebra
+                                     as kbc.py:268-296, feq recomputed per pass instead of held; rounding-level differences).
+                                     This is what 0 selects for an unforced KBC stepper.
+                               300 = KBC only: the literal three-array formulation, one cell per thread */
   const xlbn_bc_desc* bcs;  /* n_bc entries, copied */
 } xlbn_stepper_desc;
 
@@ -132,6 +134,13 @@ int xlbn_stepper_destroy(xlbn_stepper* s);
 int xlbn_stepper_set_force(xlbn_stepper* s, const double* force);
 /* Smagorinsky coefficient of an XLBN_SMAGORINSKY_LES_BGK stepper (smagorinsky_les_bgk.py:24; default 0.17). */
 int xlbn_stepper_set_smagorinsky(xlbn_stepper* s, double coefficient);
+
+/* Publish `omega` for the steps that follow (stream-ordered, no host synchronisation).  Optional on one stream: xlbn_step
+ * does it itself when omega differs from the previous call's (omega is a per-call argument of the reference kernel,
+ * nse_stepper.py:351, and may change every step).  REQUIRED before one step is issued as several xlbn_step calls on
+ * DIFFERENT streams (the slab path: face planes on a side stream, interior on the caller's): call it on a stream all of
+ * them are ordered after.  Also the form to capture inside a CUDA graph that must not depend on earlier calls. */
+int xlbn_stepper_prepare(xlbn_stepper* s, double omega, void* stream);
 
 /* One time step.  Replaces the launch in IncompressibleNavierStokesStepper.warp_implementation
  * (nse_stepper.py:385-392; kernel body 344-381) and the jitted jax_implementation_pull (147-192).
@@ -241,6 +250,12 @@ int xlbn_halo_push(xlbn_halo* h, const void* f, const xlbn_domain* dom, int time
 int xlbn_halo_signal(xlbn_halo* h, int timestep, void* stream);
 /* Make `stream` wait until both neighbours have signalled `timestep` (device-side spin, no host sync). */
 int xlbn_halo_wait(xlbn_halo* h, int timestep, void* stream);
+/* Dead-neighbour detection.  A device-side wait never hangs the GPU: after the timeout (default 120 s, environment
+ * XLBN_HALO_TIMEOUT_S, or this call) it gives up and marks the handle; from then on xlbn_step (with this halo) and every
+ * xlbn_halo_push / _signal / _wait return XLBN_E_STATE — the step that timed out read stale ghosts, so its result and
+ * everything after it is invalid and the run must stop.  xlbn_halo_timed_out: 1 if marked, 0 if not (no device sync). */
+int xlbn_halo_set_timeout(xlbn_halo* h, double seconds);
+int xlbn_halo_timed_out(xlbn_halo* h);
 /* Raw pointers for diagnostics/tests: ghost plane block [parity][face(0=lo,1=hi)][n_dir][ny][nz]. */
 int xlbn_halo_ghost_ptr(xlbn_halo* h, void** ptr, long long* bytes);
 

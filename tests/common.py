@@ -45,7 +45,9 @@ WARP_CASES = [
     "warp_channel2d_d2q9_bgk_regpressure",
     "warp_periodic_d3q27_kbc",
 ]
-# ... and the collision / forcing options the CUDA path does not have yet: oracle-only for now
+# FP32FP16 on the WARP backend (prescribed values rounded to the store dtype in f_1[0, cell]: boundary_condition.py:151)
+WARP_CASES_FP16 = ["warp_sphere_d3q19_bgk_fp32fp16", "warp_tunnel_d3q27_kbc_fp32fp16", "warp_tunnel_d3q19_bgk_zouhe_pressure_fp32fp16"]
+# ... and the collision / forcing options
 WARP_CASES_N4 = [  # one per extended instantiation of the fused kernel (csrc/step_inst_ext_*.cu)
     "warp_periodic_d3q19_bgk_forced",
     "warp_periodic_d3q19_smagorinsky",
@@ -87,8 +89,25 @@ def unpack_bits(bits, q):
 
 
 def rel_err(a, b):
+    """The norm behind every "relative" tolerance of the suite: max |a - b| / max |b| (global, i.e. relative to the largest
+    population / density / speed of the field — the w = 1/36 populations are held 12x looser than element-wise)."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def rel_err_elem(a, b, floor=1e-3):
+    """Element-relative report next to rel_err: max |a - b| / max(|b|, floor * max |b|)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float((np.abs(a - b) / np.maximum(np.abs(b), floor * max(np.abs(b).max(), 1e-300))).max())
+
+
+def fp16_ulp_histogram(a, b):
+    """{ulps: count} of |a - b| measured in fp16 units in the last place of b (both float16 arrays)."""
+    a16, b16 = np.asarray(a, dtype=np.float16), np.asarray(b, dtype=np.float16)
+    key = lambda x: np.where(x.view(np.int16) < 0, -(x.view(np.int16) & 0x7FFF).astype(np.int32), x.view(np.int16).astype(np.int32))
+    d = np.abs(key(a16) - key(b16))
+    vals, counts = np.unique(d, return_counts=True)
+    return {int(v): int(c) for v, c in zip(vals, counts)}
 
 
 # ---- oracle side ------------------------------------------------------------------------------------------------

@@ -156,9 +156,9 @@ def cavity(name, lattice, n, steps, collision="BGK", omega=1.0, solid_block=None
     run_and_save(name, dict(lattice=lattice, collision=collision, shape=np.array(shape)), stepper, meta, steps, omega, vs.d, solid255=solid)
 
 
-def tunnel(name, lattice, shape, steps, collision, omega, inlet="regularized", outlet="outflow", constant_inlet=None):
+def tunnel(name, lattice, shape, steps, collision, omega, inlet="regularized", outlet="outflow", constant_inlet=None, policy="FP32FP32"):
     """examples/cfd/flow_past_sphere_3d.py:41-109 on the WARP backend (per-cell wp.func inlet profile, L86-99)."""
-    vs, pp = init(lattice)
+    vs, pp = init(lattice, policy)
     d = vs.d
     u_max = 0.04
     grid = grid_factory(shape)
@@ -336,3 +336,11 @@ if __name__ == "__main__":
                 mesh_masks(n, lattice, (12, 11, 10), body)
     if want("warp_periodic_d2q9_kbc_forced"):
         periodic("warp_periodic_d2q9_kbc_forced", "D2Q9", (10, 12), 12, "KBC", 1.8, force=(1e-5, 1e-5))
+    # FP32FP16 on the WARP backend: the prescribed inlet value lives in f_1[0, cell] in the STORE dtype (boundary_condition.py:151,
+    # bc_zouhe.py:95-98), every load / store carries an explicit compute_dtype(...) / store_dtype(...) cast in the reference source
+    if want("warp_sphere_d3q19_bgk_fp32fp16"):
+        tunnel("warp_sphere_d3q19_bgk_fp32fp16", "D3Q19", (32, 14, 14), 30, "BGK", 1.5, policy="FP32FP16")
+    if want("warp_tunnel_d3q27_kbc_fp32fp16"):
+        tunnel("warp_tunnel_d3q27_kbc_fp32fp16", "D3Q27", (24, 12, 12), 20, "KBC", 1.6, policy="FP32FP16")
+    if want("warp_tunnel_d3q19_bgk_zouhe_pressure_fp32fp16"):
+        tunnel("warp_tunnel_d3q19_bgk_zouhe_pressure_fp32fp16", "D3Q19", (20, 10, 10), 20, "BGK", 1.4, inlet="zouhe", outlet="pressure", constant_inlet=0.03, policy="FP32FP16")

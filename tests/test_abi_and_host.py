@@ -205,7 +205,9 @@ def test_new_entry_points_validate_their_arguments_without_a_device():
     assert lib.xlbn_mask_mesh(native.D3Q19, None, 1, 1, 0, dims, one, one, one, None) < 0 and "NULL argument" in err()
     assert lib.xlbn_mask_mesh(native.D3Q19, one, 1, 255, 0, dims, one, one, one, None) < 0 and "id 255" in err()
     assert lib.xlbn_mask_mesh(native.D3Q19, one, 1, 1, 7, dims, one, one, one, None) < 0 and "edge_test 7" in err()
-    # stepper setters on a NULL handle
+    # stepper setters / prepare / halo liveness calls on a NULL handle
+    assert lib.xlbn_stepper_prepare(None, 1.0, None) < 0 and "NULL stepper" in err()
+    assert lib.xlbn_halo_set_timeout(None, 1.0) < 0 and lib.xlbn_halo_timed_out(None) < 0
     assert lib.xlbn_stepper_set_force(None, (C.c_double * 3)(1e-5, 0.0, 0.0)) < 0 and "NULL stepper" in err()
     assert lib.xlbn_stepper_set_smagorinsky(None, 0.17) < 0 and "NULL stepper" in err()
     # stepper_create argument checks for the new options (they fail before cudaMalloc)
@@ -213,6 +215,6 @@ def test_new_entry_points_validate_their_arguments_without_a_device():
     desc = native.StepperDesc(lattice=native.D2Q9, collision=native.SMAGORINSKY_LES_BGK, compute_dtype=native.F32, store_dtype=native.F32, n_bc=0, cells_per_thread=0, bcs=None)
     assert lib.xlbn_stepper_create(C.byref(desc), C.byref(out)) < 0 and "3-D velocity sets only" in err()
     desc = native.StepperDesc(lattice=native.D3Q19, collision=native.BGK, compute_dtype=native.F32, store_dtype=native.F32, n_bc=0, cells_per_thread=301, bcs=None)
-    assert lib.xlbn_stepper_create(C.byref(desc), C.byref(out)) < 0 and "lean KBC" in err()
+    assert lib.xlbn_stepper_create(C.byref(desc), C.byref(out)) < 0 and "selects a KBC formulation" in err()
     desc = native.StepperDesc(lattice=native.D3Q19, collision=5, compute_dtype=native.F32, store_dtype=native.F32, n_bc=0, cells_per_thread=0, bcs=None)
     assert lib.xlbn_stepper_create(C.byref(desc), C.byref(out)) < 0 and "unknown collision" in err()

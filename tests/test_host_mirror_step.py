@@ -15,7 +15,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from common import LATE_CASES, RTOL, STEP_CASES, WARP_CASES, WARP_CASES_N4, load_golden, oracle_masks, rel_err
+from common import LATE_CASES, RTOL, STEP_CASES, WARP_CASES, WARP_CASES_FP16, WARP_CASES_N4, load_golden, oracle_masks, rel_err
 from oracle import lbm_c
 from oracle import lbm_numpy as O
 
@@ -211,7 +211,7 @@ def test_bc_kind_codes_agree_with_the_header():
     assert lbm_c._ZOUHE[("zouhe", "velocity")] == native.BC_ZOUHE_VELOCITY and lbm_c._ZOUHE[("regularized", "pressure")] == native.BC_REGULARIZED_PRESSURE
 
 
-@pytest.mark.parametrize("name", STEP_CASES + LATE_CASES + WARP_CASES + WARP_CASES_N4)
+@pytest.mark.parametrize("name", STEP_CASES + LATE_CASES + WARP_CASES + WARP_CASES_FP16 + WARP_CASES_N4)
 def test_kernel_source_on_the_host_matches_the_reference_vectors(mirror, name):
     g = load_golden(name)
     f = mirror_run(mirror, g)

@@ -166,3 +166,76 @@ def test_voxelised_surface_is_conservative_and_watertight(body):
         near |= nb
         assert np.array_equal(mm[lat.opp[l]], nb & ~solid)
     assert np.array_equal(bm[0] == 7, near & ~solid)
+
+
+# ---- the CUDA voxeliser (xlbn_mask_mesh through MeshBoundaryMasker) ---------------------------------------------------------------
+
+
+def _gpu_mesh_env(lattice):
+    import xlb_b200 as xlb
+    from xlb_b200.compute_backend import ComputeBackend
+
+    pp, be = xlb.PrecisionPolicy.FP32FP32, ComputeBackend.WARP
+    vs = getattr(xlb.velocity_set, lattice)(pp, be)
+    xlb.init(velocity_set=vs, default_backend=be, default_precision_policy=pp)
+    return xlb, vs, pp, be
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["reference", "schwarz_seidel"])
+@pytest.mark.parametrize("name", MESH_CASES)
+def test_cuda_mesh_masker_equals_the_oracle_and_the_reference_masks(name, mode):
+    """Both edge tests vs the oracle; the literal one also vs the masks the reference's own kernel produced."""
+    from xlb_b200.grid import grid_factory
+    from xlb_b200.operator.boundary_condition import HalfwayBounceBackBC
+    from xlb_b200.operator.boundary_masker import MeshBoundaryMasker
+
+    g = load_mesh_case(name)
+    lattice, shape = str(g["lattice"]), tuple(int(s) for s in g["shape"])
+    xlb, vs, pp, be = _gpu_mesh_env(lattice)
+    grid = grid_factory(shape)
+    lat = O.Lattice(lattice)
+    bc = HalfwayBounceBackBC(mesh_vertices=g["vertices"].copy())
+    bc.id = int(g["bc_id"])
+    bc_mask = grid.create_field(cardinality=1, dtype=xlb.Precision.UINT8)
+    missing = grid.create_field(cardinality=vs.q, dtype=xlb.Precision.BOOL)
+    bc_mask, missing = MeshBoundaryMasker(vs, pp, be, edge_test=mode)(bc, bc_mask, missing)
+    bm, mm = O.build_masks_mesh(g["vertices"], bc.id, np.zeros((1,) + shape, np.uint8), np.zeros((lat.q,) + shape, bool), lat, edge_test=mode)
+    assert np.array_equal(bc_mask.numpy(), bm) and np.array_equal(missing.numpy(), mm)
+    if mode == "reference":
+        assert np.array_equal(bc_mask.numpy(), g["bc_mask"]) and np.array_equal(missing.numpy(), unpack_bits(g["missing_bits"], lat.q))
+
+
+@pytest.mark.gpu
+def test_cuda_wind_tunnel_with_a_mesh_body_against_the_c_oracle():
+    """examples/cfd/windtunnel_3d.py:66-96 in small: Fullway walls, Regularized inlet, ExtrapolationOutflow, Halfway mesh body, D3Q27 KBC;
+    masks bit-exact vs the oracle voxeliser, 20 steps vs the C oracle on the same masks."""
+    from common import rel_err
+    from oracle import lbm_c
+    from xlb_b200.grid import grid_factory
+    from xlb_b200.operator.boundary_condition import ExtrapolationOutflowBC, FullwayBounceBackBC, HalfwayBounceBackBC, RegularizedBC
+    from xlb_b200.operator.stepper import IncompressibleNavierStokesStepper
+
+    g = load_mesh_case("warp_mesh_octahedron_d3q27")
+    shape = (24, 11, 10)
+    xlb, vs, pp, be = _gpu_mesh_env("D3Q27")
+    grid = grid_factory(shape)
+    box, bne = grid.bounding_box_indices(), grid.bounding_box_indices(remove_edges=True)
+    walls = [box["bottom"][i] + box["top"][i] + box["front"][i] + box["back"][i] for i in range(3)]
+    walls = np.unique(np.array(walls), axis=-1).tolist()
+    verts = g["vertices"] + np.array([2.0, 0.0, 0.0])
+    bcs = [FullwayBounceBackBC(indices=walls), RegularizedBC("velocity", prescribed_value=(0.03, 0.0, 0.0), indices=bne["left"]),
+           ExtrapolationOutflowBC(indices=bne["right"]), HalfwayBounceBackBC(mesh_vertices=verts.copy())]  # fmt: skip
+    stepper = IncompressibleNavierStokesStepper(grid=grid, boundary_conditions=bcs, collision_type="KBC")
+    f_0, f_1, bc_mask, missing = stepper.prepare_fields()
+    lat = O.Lattice("D3Q27")
+    obcs = [O.BC("fullway", bcs[0].id, np.array(walls)), O.BC("regularized", bcs[1].id, np.array(bne["left"]), bc_type="velocity", prescribed=np.array([0.03, 0.0, 0.0])),
+            O.BC("outflow", bcs[2].id, np.array(bne["right"])), O.BC("halfway", bcs[3].id, np.zeros((3, 0), np.int64))]  # fmt: skip
+    bm, mm = O.build_masks(obcs[:3], shape, lat, flavor="warp")
+    bm, mm = O.build_masks_mesh(verts, bcs[3].id, bm, mm, lat)
+    assert np.array_equal(bc_mask.numpy(), bm) and np.array_equal(missing.numpy(), mm)
+    for i in range(20):
+        f_0, f_1 = stepper(f_0, f_1, bc_mask, missing, 1.6, i)
+        f_0, f_1 = f_1, f_0
+    err = rel_err(f_0.numpy(), lbm_c.run(O.initialize_eq(shape, lat), bm, mm, obcs, 1.6, lat, 20, "FP32FP32", "KBC"))
+    assert err <= 1e-5, err

@@ -1,0 +1,124 @@
+"""1000-step parity runs of the fused CUDA step against the C/OpenMP restatement of the reference's fused Warp kernel
+(oracle/lbm_ref.c; pinned bit for bit against the reference's own WARP backend, tests/test_warp_path_golden.py).
+
+North-star gates: populations, rho and u within 1e-5 relative (fp32) / 1e-3 (fp16 storage) after 1000 steps — the loop of
+examples/performance/mlups_3d.py:77-80.  "Relative" = max |a - b| / max |b| (tests/common.py rel_err); the element-relative figure
+and, for fp16 storage, the histogram of the differences in fp16 units in the last place are printed next to it.
+
+  * C1 literally: lid-driven cavity D3Q19 BGK 128^3 FP32FP32, omega = 1, 1000 steps (BASELINE configs[0]),
+  * FP32FP16 storage: the cavity at 64^3 and a periodic Taylor-Green vortex at 64^3, 1000 steps,
+  * C3 at the example's own size: flow past a sphere D3Q27 KBC 256x64x64, 1000 steps (default = lean KBC, and the literal form)."""
+
+import functools
+
+import numpy as np
+import pytest
+
+from common import fp16_ulp_histogram, load_golden, native_run, oracle_bcs, rel_err, rel_err_elem
+from oracle import lbm_c
+from oracle import lbm_numpy as O
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not lbm_c.available(), reason="oracle/liblbm_ref.so not built (make -C oracle)")]
+STEPS = 1000
+
+
+def compare(name, f, ref, lat, tol, u_scale):
+    rho_r, u_r = O.macroscopic(ref.astype(np.float64), lat)
+    rho_n, u_n = O.macroscopic(f.astype(np.float64), lat)
+    e_f, e_rho, e_u = rel_err(f, ref), rel_err(rho_n, rho_r), float(np.abs(u_n - u_r).max() / max(np.abs(u_r).max(), u_scale))
+    line = f"{name}: f {e_f:.3e} (element-relative {rel_err_elem(f, ref):.3e})  rho {e_rho:.3e}  u {e_u:.3e}"
+    if f.dtype == np.float16:
+        h = fp16_ulp_histogram(f, ref)
+        line += f"  fp16 ulps {dict(sorted(h.items())[:6])} max {max(h)}"
+    print(line)
+    assert np.isfinite(f.astype(np.float64)).all()
+    assert e_f <= tol and e_rho <= tol and e_u <= tol, line
+
+
+@functools.lru_cache(maxsize=None)
+def cavity_reference(n, policy):
+    lat, shape, bcs, bc_mask, missing = lbm_c.cavity_case("D3Q19", n, policy)
+    f_init = O.initialize_eq(shape, lat, policy)
+    return lat, shape, bcs, bc_mask, missing, f_init, lbm_c.run(f_init, bc_mask, missing, bcs, 1.0, lat, STEPS, policy)
+
+
+def run_cavity(n, policy, v=0):
+    lat, shape, bcs, bc_mask, missing, f_init, ref = cavity_reference(n, policy)
+    g = load_golden("cavity_d3q19_bgk_fp32")
+    g.update(shape=shape, steps=STEPS, omega=1.0, f_init=f_init, policy=policy)
+    g["bcs"] = [dict(kind="equilibrium", id=1, indices=bcs[0].indices, rho=1.0, u=np.array([0.02, 0, 0])), dict(kind="fullway", id=2, indices=bcs[1].indices)]
+    f, bm, mm = native_run(g, cells_per_thread=v)
+    assert np.array_equal(bm, bc_mask) and np.array_equal(mm, missing), "masks must be bit-exact"
+    return f, ref, lat
+
+
+def test_c1_cavity_128_fp32_1000_steps():
+    """BASELINE configs[0]: the C1 run itself."""
+    f, ref, lat = run_cavity(128, "FP32FP32")
+    compare("C1 cavity 128^3 FP32FP32", f, ref, lat, 1e-5, 0.02)
+
+
+@pytest.mark.parametrize("v", [0, 1])  # 0 = half2-state pair path (default), 1 = scalar path
+def test_cavity_64_fp16_storage_1000_steps(v):
+    f, ref, lat = run_cavity(64, "FP32FP16", v)
+    compare(f"cavity 64^3 FP32FP16 v={v}", f, ref, lat, 1e-3, 0.02)
+
+
+@functools.lru_cache(maxsize=None)
+def taylor_green(n, policy, lattice, collision, omega):
+    lat = O.Lattice(lattice)
+    shape = (n, n, n)
+    k = 2.0 * np.pi / n
+    X, Y, Z = np.meshgrid(*[k * (np.arange(n) + 0.5)] * 3, indexing="ij")
+    u0 = 0.04
+    u = np.stack([u0 * np.sin(X) * np.cos(Y) * np.cos(Z), -u0 * np.cos(X) * np.sin(Y) * np.cos(Z), np.zeros_like(X)])
+    rho = 1.0 + (3.0 * u0 * u0 / 16.0) * (np.cos(2 * X) + np.cos(2 * Y)) * (np.cos(2 * Z) + 2.0)
+    f_init = O.initialize_eq(shape, lat, policy, rho=rho[None], u=u)
+    bc_mask, missing = np.zeros((1,) + shape, np.uint8), np.zeros((lat.q,) + shape, bool)
+    ref = lbm_c.run(f_init, bc_mask, missing, [], omega, lat, STEPS, policy, collision)
+    return lat, shape, f_init, ref
+
+
+@pytest.mark.parametrize("policy,tol", [("FP32FP16", 1e-3), ("FP32FP32", 1e-5)])
+def test_taylor_green_64_1000_steps(policy, tol):
+    """Periodic Taylor-Green vortex (no boundary at all: every cell takes the straight-line path), D3Q19 BGK, omega 1.7."""
+    lat, shape, f_init, ref = taylor_green(64, policy, "D3Q19", "BGK", 1.7)
+    g = load_golden("periodic_d3q19_bgk_fp32")
+    g.update(shape=shape, steps=STEPS, omega=1.7, policy=policy, f_init=f_init, bcs=[], n_bc=0)
+    f, _, _ = native_run(g)
+    compare(f"Taylor-Green 64^3 {policy}", f, ref, lat, tol, 0.04)
+
+
+@functools.lru_cache(maxsize=None)
+def sphere_reference():
+    shape, lat = (256, 64, 64), O.Lattice("D3Q27")
+    box, bne = O.bounding_box_indices(shape), O.bounding_box_indices(shape, remove_edges=True)
+    walls = np.unique(np.concatenate([box[k] for k in ("bottom", "top", "front", "back")], axis=1), axis=-1)
+    X, Y, Z = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+    sph = np.array(np.where((X - shape[0] // 6) ** 2 + (Y - shape[1] // 2) ** 2 + (Z - shape[2] // 2) ** 2 < (shape[1] // 12) ** 2))
+    Hy, Hz = float(shape[1] - 1), float(shape[2] - 1)
+    yy, zz = np.meshgrid(np.arange(shape[1]), np.arange(shape[2]), indexing="ij")
+    ux = (0.04 * np.maximum(0.0, 1.0 - ((2.0 * (yy - Hy / 2.0) / Hy) ** 2.0 + (2.0 * (zz - Hz / 2.0) / Hz) ** 2.0))).astype(np.float32)
+    pv = np.stack([ux, np.zeros_like(ux), np.zeros_like(ux)])
+    g = load_golden("sphere_d3q27_kbc_fp32")
+    g.update(shape=shape, steps=STEPS, omega=1.6, f_init=O.initialize_eq(shape, lat))
+    g["bcs"] = [
+        dict(kind="fullway", id=1, indices=walls),
+        dict(kind="regularized", id=2, indices=bne["left"], bc_type="velocity", prescribed=pv),
+        dict(kind="outflow", id=3, indices=bne["right"]),
+        dict(kind="halfway", id=4, indices=sph),
+    ]
+    bcs = oracle_bcs(g)
+    bc_mask, missing = O.build_masks(bcs, shape, lat, flavor="warp")
+    ref = lbm_c.run(g["f_init"], bc_mask, missing, bcs, 1.6, lat, STEPS, "FP32FP32", "KBC")
+    return g, lat, bc_mask, missing, ref
+
+
+@pytest.mark.parametrize("v", [0, 300])  # 0 = register-lean KBC (default), 300 = the literal formulation
+def test_c3_sphere_d3q27_kbc_256x64x64_1000_steps(v):
+    """BASELINE configs[2] at the reference example's own size (examples/cfd/flow_past_sphere_3d.py:22): D3Q27 KBC omega 1.6,
+    Fullway walls, Regularized Poiseuille inlet, ExtrapolationOutflow outlet, Halfway sphere."""
+    g, lat, bc_mask, missing, ref = sphere_reference()
+    f, bm, mm = native_run(g, cells_per_thread=v)
+    assert np.array_equal(bm, bc_mask) and np.array_equal(mm, missing), "masks must be bit-exact"
+    compare(f"C3 sphere 256x64x64 D3Q27 KBC v={v}", f, ref, lat, 1e-5, 0.04)

@@ -239,3 +239,48 @@ def test_momentum_transfer_matches_reference_vectors(name, backend):
     force = force.numpy() if hasattr(force, "numpy") and not isinstance(force, np.ndarray) else np.asarray(force)
     assert force.shape == (3,)
     assert np.allclose(force, g["force"], rtol=2e-5, atol=1e-7), (force, g["force"])
+
+
+@pytest.mark.parametrize("lattice", ["D3Q19", "D3Q27", "D2Q9"])
+def test_extended_collision_operators_standalone(lattice):
+    """SmagorinskyLESBGK / ForcedCollision / ExactDifference through the operator classes (xlbn_collide_ext, xlbn_exact_difference;
+    reference: smagorinsky_les_bgk.py:92-138, forced_collision.py:46-50, exact_difference_force.py:79-84) vs the numpy oracle on a
+    seeded random state.  Two gates per operator: the full populations at 5e-7 relative (a few fp32 ulps of f), and the
+    operator's INCREMENT (out - f) at the same absolute bound — the ExactDifference increment itself is only ~3e-5 |f|, so a
+    bound relative to the increment would sit below one ulp of the populations it is added to (round 1's mistake)."""
+    from oracle import lbm_numpy as O
+    from xlb_b200.operator.collision import ForcedCollision, SmagorinskyLESBGK
+    from xlb_b200.operator.force import ExactDifference
+
+    vs = init_xlb_env(lattice)
+    lat = O.Lattice(lattice)
+    shape = (6, 5, 4) if lat.d == 3 else (9, 7)
+    rng = np.random.default_rng(3)
+    rho = (1.0 + 0.01 * rng.standard_normal((1,) + shape)).astype(np.float32)
+    u = (0.03 * rng.standard_normal((lat.d,) + shape)).astype(np.float32)
+    feq = O.equilibrium(rho, u, lat)
+    f = (feq * (1.0 + 0.02 * rng.standard_normal(feq.shape))).astype(np.float32)
+    force = np.array([2e-4, -1e-4, 5e-5][: lat.d])
+    dev = lambda a: torch.as_tensor(a if lat.d == 3 else a[..., None]).cuda()
+    back = lambda t: t.cpu().numpy() if lat.d == 3 else t.cpu().numpy()[..., 0]
+    F, FEQ, RHO, U = dev(f), dev(feq), dev(rho), dev(u)
+    scale = np.abs(f).max()
+
+    def check(name, got, want):
+        got = back(got)
+        assert rel_err(got, want) <= 5e-7, f"{lattice} {name}: full rel err {rel_err(got, want):.2e}"
+        assert np.abs((got - f) - (want - f)).max() <= 5e-7 * scale, f"{lattice} {name}: increment"
+        assert np.abs(want - f).max() > 0, name  # the operator did something
+
+    check("ExactDifference", ExactDifference(force)(F, FEQ, torch.empty_like(F), RHO, U), O.exact_difference_force(f.copy(), feq, rho, u, force, lat))
+    cases = [("BGK", BGK)] + ([("KBC", KBC)] if lattice != "D3Q19" else []) + ([("SmagorinskyLESBGK", SmagorinskyLESBGK)] if lat.d == 3 else [])
+    for cname, cls in cases:
+        if cname == "BGK":
+            base = O.collide_bgk(f, feq, 1.7)
+        elif cname == "KBC":
+            base = O.collide_kbc(f, feq, rho, lat, 1.7)
+        else:
+            base = O.collide_smagorinsky(f, feq, lat, 1.7)
+            check(cname, cls()(F, FEQ, RHO, U, torch.empty_like(F), 1.7), base)
+        want = O.exact_difference_force(base, feq, rho, u, force, lat)
+        check("Forced" + cname, ForcedCollision(cls(), force_vector=force)(F, FEQ, torch.empty_like(F), RHO, U, 1.7), want)

@@ -97,32 +97,7 @@ def test_stepper_errors_are_loud():
         stepper(f_0.to(torch.float16), f_1, bc_mask, missing_mask, 1.0, 0)
 
 
-@pytest.mark.parametrize("n", [128 if __import__("os").environ.get("XLB_FULL_C1") else 64])
-def test_c1_cavity_1000_steps_against_c_oracle(n):
-    """BASELINE config C1: lid-driven cavity D3Q19 BGK FP32FP32, omega = 1, 1000 steps (examples/performance/mlups_3d.py),
-    against the C/OpenMP restatement of the reference's fused kernel.  128^3 with XLB_FULL_C1=1 (minutes of CPU time),
-    64^3 by default.  Masks bit-exact; f, rho, u within 1e-5 relative (north-star tolerance)."""
-    from oracle import lbm_c
-    from oracle import lbm_numpy as O
-
-    if not lbm_c.available():
-        pytest.skip("oracle/liblbm_ref.so not built")
-    lat, shape, bcs, bc_mask, missing = lbm_c.cavity_case("D3Q19", n, "FP32FP32")
-    f_init = O.initialize_eq(shape, lat)
-    ref = lbm_c.run(f_init, bc_mask, missing, bcs, 1.0, lat, 1000)
-    g = load_golden("cavity_d3q19_bgk_fp32")
-    g.update(shape=shape, steps=1000, omega=1.0, f_init=f_init)
-    g["bcs"] = [dict(kind="equilibrium", id=1, indices=bcs[0].indices, rho=1.0, u=np.array([0.02, 0, 0])), dict(kind="fullway", id=2, indices=bcs[1].indices)]
-    f, bm, mm = native_run(g)
-    assert np.array_equal(bm, bc_mask) and np.array_equal(mm, missing)
-    assert rel_err(f, ref) <= 1e-5, rel_err(f, ref)
-    rho_r, u_r = O.macroscopic(ref, lat)
-    rho_n, u_n = O.macroscopic(f, lat)
-    assert rel_err(rho_n, rho_r) <= 1e-5
-    assert np.abs(u_n - u_r).max() <= 1e-5 * 0.02
-
-
-@pytest.mark.parametrize("v", [0, 1, 102])
+@pytest.mark.parametrize("v", [1, 102])
 def test_c3_sphere_d3q27_kbc_256x64x64_against_c_oracle(v):
     """BASELINE config C3 at the reference example's own size (examples/cfd/flow_past_sphere_3d.py:22: 256x64x64):
     D3Q27 KBC omega 1.6, Fullway walls, Regularized Poiseuille inlet, ExtrapolationOutflow outlet, Halfway sphere.

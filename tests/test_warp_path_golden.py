@@ -6,7 +6,7 @@ FOR BIT on every case (asserted); the numpy oracle follows the JAX path (differe
 import numpy as np
 import pytest
 
-from common import WARP_CASES, WARP_CASES_N4, c_oracle_run, load_golden, oracle_masks, oracle_run, rel_err, unpack_bits
+from common import RTOL, WARP_CASES, WARP_CASES_FP16, WARP_CASES_N4, c_oracle_run, load_golden, oracle_masks, oracle_run, rel_err, unpack_bits
 from oracle import lbm_c
 from oracle import lbm_numpy as O
 
@@ -26,6 +26,18 @@ def test_numpy_oracle_matches_the_warp_backend(name):
     f, bc_mask, missing = oracle_run(g, flavor="warp")
     check_masks(g, bc_mask, missing)
     assert rel_err(f, g["f_final"]) <= (2e-6 if g["policy"] == "FP32FP32" else 1e-13)
+
+
+@needs_c
+@pytest.mark.parametrize("name", WARP_CASES_FP16)
+def test_c_oracle_matches_the_warp_backend_under_fp16_storage(name):
+    """FP32FP16 on the WARP backend: prescribed values rounded to fp16 in f_1[0, cell] (boundary_condition.py:151), every load widened,
+    every store narrowed by the reference's explicit casts.  Bit for bit."""
+    g = load_golden(name)
+    assert g["backend"] == "WARP" and g["policy"] == "FP32FP16" and g["f_final"].dtype == np.float16
+    f, bc_mask, missing = c_oracle_run(g)
+    check_masks(g, bc_mask, missing)
+    assert np.array_equal(f, g["f_final"]), rel_err(f, g["f_final"])
 
 
 @needs_c

@@ -19,6 +19,25 @@ struct xlbn_stepper {
 
 using namespace xlbn;
 
+namespace {
+// Makes `device` current for the duration of a call when it is not already (one cudaGetDevice per call otherwise).
+struct DeviceGuard {
+  int previous = -1;
+  cudaError_t error = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    int current = -1;
+    error = cudaGetDevice(&current);
+    if (error == cudaSuccess && current != device) {
+      error = cudaSetDevice(device);
+      if (error == cudaSuccess) previous = current;
+    }
+  }
+  ~DeviceGuard() {
+    if (previous >= 0) cudaSetDevice(previous);
+  }
+};
+}  // namespace
+
 namespace xlbn {
 template <> int dispatch_step<D3Q19, XLBN_BGK>(const StepCall&);
 template <> int dispatch_step<D3Q27, XLBN_BGK>(const StepCall&);
@@ -79,9 +98,10 @@ int xlbn_stepper_create(const xlbn_stepper_desc* desc, xlbn_stepper** out) {
   if (desc->compute_dtype == XLBN_F32 && desc->store_dtype == XLBN_F64) return fail(XLBN_E_DTYPE, "stepper_create: no FP32FP64 policy");
   if (desc->n_bc < 0 || (desc->n_bc > 0 && !desc->bcs)) return fail(XLBN_E_ARG, "stepper_create: bad BC list");
   const int cpt = desc->cells_per_thread;
-  if (cpt != 0 && cpt != 1 && cpt != 2 && cpt != 4 && cpt != 8 && cpt != 102 && cpt != 104 && cpt != 202 && cpt != 203 && cpt != 301)
+  if (cpt != 0 && cpt != 1 && cpt != 2 && cpt != 4 && cpt != 8 && cpt != 102 && cpt != 104 && cpt != 202 && cpt != 203 && cpt != 300 && cpt != 301)
     return fail(XLBN_E_ARG, "stepper_create: cells_per_thread = %d", cpt);
-  if (cpt == 301 && desc->collision != XLBN_KBC) return fail(XLBN_E_ARG, "stepper_create: cells_per_thread = 301 selects the lean KBC collision; the stepper's collision is %d", desc->collision);
+  if ((cpt == 300 || cpt == 301) && desc->collision != XLBN_KBC)
+    return fail(XLBN_E_ARG, "stepper_create: cells_per_thread = %d selects a KBC formulation; the stepper's collision is %d", cpt, desc->collision);
 
   BcEntry host[256];
   memset(host, 0, sizeof(host));
@@ -147,6 +167,23 @@ int xlbn_stepper_set_smagorinsky(xlbn_stepper* s, double coefficient) {
   return 0;
 }
 
+int xlbn_stepper_prepare(xlbn_stepper* s, double omega, void* stream) {
+  if (!s) return fail(XLBN_E_ARG, "stepper_prepare: NULL stepper");
+  // only the FP32FP16 BGK pair path reads per-omega constants (BcEntry::eq_out of EquilibriumBC entries)
+  if (!s->has_equilibrium_bc || s->compute_dtype != XLBN_F32 || s->store_dtype != XLBN_F16 || s->collision != XLBN_BGK || s->forced) return 0;
+  DeviceGuard guard(s->device);
+  if (guard.error != cudaSuccess) return cuda_fail(guard.error, "stepper_prepare: cudaSetDevice");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (s->lattice) {
+    case XLBN_D2Q9: bc_precompute_kernel<D2Q9, XLBN_BGK><<<1, 256, 0, st>>>(s->table, (float)omega); break;
+    case XLBN_D3Q19: bc_precompute_kernel<D3Q19, XLBN_BGK><<<1, 256, 0, st>>>(s->table, (float)omega); break;
+    default: bc_precompute_kernel<D3Q27, XLBN_BGK><<<1, 256, 0, st>>>(s->table, (float)omega); break;
+  }
+  XLBN_LAUNCH_OK("bc_precompute_kernel");
+  s->eq_omega = omega;
+  return 0;
+}
+
 int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask, const uint32_t* missing_bits, const xlbn_domain* dom, double omega,
               int timestep, xlbn_halo* halo, void* stream) {
   if (!s || !f0 || !f1 || !bc_mask || !dom) return fail(XLBN_E_ARG, "xlbn_step: NULL argument");
@@ -157,18 +194,20 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
     return fail(XLBN_E_SHAPE, "xlbn_step: x range [%d, %d) outside [0, %d)", dom->x_begin, dom->x_begin + dom->x_count, dom->nx);
   if (s->lattice == XLBN_D2Q9 && dom->nz != 1) return fail(XLBN_E_SHAPE, "xlbn_step: 2-D lattice needs nz == 1");
   if (dom->x_count == 0) return 0;
+  DeviceGuard guard(s->device);  // the BC table lives on the device the stepper was created on; launch there
+  if (guard.error != cudaSuccess) return cuda_fail(guard.error, "xlbn_step: cudaSetDevice");
 
   StepCall c;
   c.compute_dtype = s->compute_dtype;
   c.store_dtype = s->store_dtype;
-  c.requested_v = s->cells_per_thread;
+  c.requested_v = s->cells_per_thread == 300 ? 1 : s->cells_per_thread;
   c.f0 = f0;
   c.f1 = f1;
   c.bc = bc_mask;
   c.miss = missing_bits;
   c.table = s->table;
   c.table_rw = s->table;
-  // EquilibriumBC constants (read by the FP32FP16 pair path only) follow omega; refreshing them synchronises the stream
+  // EquilibriumBC constants (read by the FP32FP16 pair path only) follow omega; refreshed stream-ordered when it changes
   c.eq_omega_state = s->has_equilibrium_bc ? &s->eq_omega : nullptr;
   c.kinds = s->kinds;
   c.omega = omega;
@@ -194,6 +233,7 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
   }
   if (halo) {
     if (!halo->connected) return fail(XLBN_E_STATE, "xlbn_step: halo is not connected");
+    if (int e = halo_check_alive(halo, "xlbn_step")) return e;
     if (halo->lattice != s->lattice || halo->store_dtype != s->store_dtype || halo->ny != dom->ny || halo->nz != dom->nz)
       return fail(XLBN_E_SHAPE, "xlbn_step: halo does not match the stepper / domain");
     const int p_in = timestep & 1, p_out = (timestep + 1) & 1;
@@ -203,7 +243,9 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
     c.out_lo = halo_ghost(halo, halo->peer_lo, p_out, 1);
   }
   if (s->cells_per_thread == 301 && s->forced) return fail(XLBN_E_UNSUPPORTED, "xlbn_step: the lean KBC variant (cells_per_thread = 301) has no forced form");
-  const int coll = s->collision | (s->forced ? kF : 0) | (s->cells_per_thread == 301 ? kLeanKbc : 0);
+  // KBC: the register-lean formulation is the default (B200: 0.81 vs 0.69 of the HBM roofline, profiles/r2_*); 300 = literal
+  const bool lean = s->collision == XLBN_KBC && !s->forced && (s->cells_per_thread == 0 || s->cells_per_thread == 301);
+  const int coll = s->collision | (s->forced ? kF : 0) | (lean ? kLeanKbc : 0);
   switch (s->lattice) {
     case XLBN_D3Q19:
       switch (coll) {

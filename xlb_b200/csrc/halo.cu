@@ -15,6 +15,7 @@
 #include "halo.cuh"
 #include "lbm_math.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace xlbn {
@@ -50,17 +51,35 @@ __global__ void halo_signal_kernel(int* flag_a, int* flag_b, int value) {
   __threadfence_system();
 }
 
-__global__ void halo_wait_kernel(int* flags, int value) {
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Never hangs the GPU: after timeout_ns the wait gives up, marks the handle dead (flags[2] on the device and *timed_out in
+// mapped host memory, value = step + 1) and lets the stream drain; the host side then refuses every further call.
+__global__ void halo_wait_kernel(int* flags, int value, long long timeout_ns, int* timed_out) {
   volatile int* f = flags;
-  const long long t0 = clock64();
+  const long long t0 = global_ns();
   while (f[0] < value || f[1] < value) {
-    if (clock64() - t0 > 20000000000LL) {  // ~10 s: never hang the GPU; the host checks flags[2]
-      f[2] = 1;
+    if (global_ns() - t0 > timeout_ns) {
+      f[2] = value + 1;
+      *reinterpret_cast<volatile int*>(timed_out) = value + 1;
       break;
     }
     __nanosleep(200);
   }
   __threadfence_system();
+}
+
+int halo_check_alive(const xlbn_halo* h, const char* where) {
+  if (h->timed_out && *h->timed_out != 0)
+    return fail(XLBN_E_STATE,
+                "%s: a ring neighbour did not deliver its face populations for step %d within %.0f s (dead or stalled rank); the ghost planes "
+                "read since then were stale, so the populations of this slab are invalid from that step on",
+                where, *h->timed_out - 1, (double)h->timeout_ns * 1e-9);
+  return 0;
 }
 
 }  // namespace xlbn
@@ -86,7 +105,20 @@ int xlbn_halo_create(int lattice, int store_dtype, int ny, int nz, xlbn_halo** o
   h->block_bytes = h->flags_offset + 256;
   h->peer_lo = h->peer_hi = nullptr;
   h->ipc_lo = h->ipc_hi = h->connected = false;
+  h->base = nullptr;
+  h->timed_out = nullptr;
+  h->timed_out_dev = nullptr;
+  h->timeout_ns = 120LL * 1000000000LL;  // default 120 s; XLBN_HALO_TIMEOUT_S or xlbn_halo_set_timeout change it
+  if (const char* env = getenv("XLBN_HALO_TIMEOUT_S")) {
+    const double sec = atof(env);
+    if (sec > 0.0) h->timeout_ns = (long long)(sec * 1e9);
+  }
   cudaError_t e = cudaGetDevice(&h->device);
+  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(const_cast<int**>(&h->timed_out)), sizeof(int), cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    *h->timed_out = 0;
+    e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->timed_out_dev), const_cast<int*>(h->timed_out), 0);
+  }
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->base), h->block_bytes);
   if (e == cudaSuccess) e = cudaMemset(h->base, 0, h->block_bytes);
   if (e == cudaSuccess) {
@@ -94,6 +126,8 @@ int xlbn_halo_create(int lattice, int store_dtype, int ny, int nz, xlbn_halo** o
     e = cudaMemcpy(halo_flags(h, h->base), init, sizeof(init), cudaMemcpyHostToDevice);
   }
   if (e != cudaSuccess) {
+    if (h->base) cudaFree(h->base);
+    if (h->timed_out) cudaFreeHost(const_cast<int*>(h->timed_out));
     delete h;
     return cuda_fail(e, "halo_create");
   }
@@ -106,8 +140,21 @@ int xlbn_halo_destroy(xlbn_halo* h) {
   if (h->ipc_lo && h->peer_lo) cudaIpcCloseMemHandle(h->peer_lo);
   if (h->ipc_hi && h->peer_hi && h->peer_hi != h->peer_lo) cudaIpcCloseMemHandle(h->peer_hi);
   if (h->base) cudaFree(h->base);
+  if (h->timed_out) cudaFreeHost(const_cast<int*>(h->timed_out));
   delete h;
   return 0;
+}
+
+int xlbn_halo_set_timeout(xlbn_halo* h, double seconds) {
+  if (!h) return fail(XLBN_E_ARG, "halo_set_timeout: NULL");
+  if (!(seconds > 0.0)) return fail(XLBN_E_ARG, "halo_set_timeout: %g s", seconds);
+  h->timeout_ns = (long long)(seconds * 1e9);
+  return 0;
+}
+
+int xlbn_halo_timed_out(xlbn_halo* h) {
+  if (!h) return fail(XLBN_E_ARG, "halo_timed_out: NULL");
+  return (h->timed_out && *h->timed_out != 0) ? 1 : 0;
 }
 
 int xlbn_halo_export(xlbn_halo* h, unsigned char handle[64]) {
@@ -146,6 +193,7 @@ int xlbn_halo_connect(xlbn_halo* h, const unsigned char lo_handle[64], const uns
 int xlbn_halo_push(xlbn_halo* h, const void* f, const xlbn_domain* dom, int timestep, void* stream) {
   if (!h || !f || !dom) return fail(XLBN_E_ARG, "halo_push: NULL");
   if (!h->connected) return fail(XLBN_E_STATE, "halo_push: halo is not connected");
+  if (int e = halo_check_alive(h, "halo_push")) return e;
   if (dom->ny != h->ny || dom->nz != h->nz || dom->nx <= 0) return fail(XLBN_E_SHAPE, "halo_push: dims do not match the halo");
   const long long plane = (long long)h->ny * h->nz;
   const long long n = plane * dom->nx;
@@ -170,6 +218,7 @@ int xlbn_halo_push(xlbn_halo* h, const void* f, const xlbn_domain* dom, int time
 int xlbn_halo_signal(xlbn_halo* h, int timestep, void* stream) {
   if (!h) return fail(XLBN_E_ARG, "halo_signal: NULL");
   if (!h->connected) return fail(XLBN_E_STATE, "halo_signal: halo is not connected");
+  if (int e = halo_check_alive(h, "halo_signal")) return e;
   // I am the hi neighbour of my lo neighbour (its flags[1]) and the lo neighbour of my hi neighbour (its flags[0])
   halo_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(halo_flags(h, h->peer_lo) + 1, halo_flags(h, h->peer_hi) + 0, timestep);
   XLBN_LAUNCH_OK("halo_signal_kernel");
@@ -179,7 +228,8 @@ int xlbn_halo_signal(xlbn_halo* h, int timestep, void* stream) {
 int xlbn_halo_wait(xlbn_halo* h, int timestep, void* stream) {
   if (!h) return fail(XLBN_E_ARG, "halo_wait: NULL");
   if (!h->connected) return fail(XLBN_E_STATE, "halo_wait: halo is not connected");
-  halo_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(halo_flags(h, h->base), timestep);
+  if (int e = halo_check_alive(h, "halo_wait")) return e;
+  halo_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(halo_flags(h, h->base), timestep, h->timeout_ns, h->timed_out_dev);
   XLBN_LAUNCH_OK("halo_wait_kernel");
   return 0;
 }

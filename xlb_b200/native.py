@@ -79,6 +79,7 @@ SIGNATURES = {
     "xlbn_stepper_destroy": [_P],
     "xlbn_stepper_set_force": [_P, C.POINTER(C.c_double)],
     "xlbn_stepper_set_smagorinsky": [_P, _D],
+    "xlbn_stepper_prepare": [_P, _D, _P],
     "xlbn_step": [_P, _P, _P, _P, _P, C.POINTER(Domain), _D, _I, _P, _P],
     "xlbn_mask_indices": [_I, _I, _P, _LL, _I, _I, Int3, Int3, Int3, _P, _P, _P, _P],
     "xlbn_mask_finalize_jax": [_I, Int3, Int3, Int3, _P, _P, _P],
@@ -101,6 +102,8 @@ SIGNATURES = {
     "xlbn_halo_push": [_P, _P, C.POINTER(Domain), _I, _P],
     "xlbn_halo_signal": [_P, _I, _P],
     "xlbn_halo_wait": [_P, _I, _P],
+    "xlbn_halo_set_timeout": [_P, _D],
+    "xlbn_halo_timed_out": [_P],
     "xlbn_halo_ghost_ptr": [_P, C.POINTER(_P), C.POINTER(_LL)],
 }
 _RESTYPE = {"xlbn_last_error": C.c_char_p}
