@@ -43,6 +43,8 @@ def parse():
     p.add_argument("--policy", default="FP32FP32", choices=list(STORE_BYTES))
     p.add_argument("--config", default="cavity", choices=["cavity", "periodic", "sphere", "tunnel"])
     p.add_argument("--cells-per-thread", type=int, default=0)
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1: weak = n^3 per GPU (x-slabs), strong = the N = 1 grid split over N GPUs")
+    p.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (FP32FP16 cavity, D3Q27 KBC cavity, C3 sphere) appended at N = 1")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--e2e-steps", type=int, default=0)
@@ -57,9 +59,12 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Started before the warm-up (the
+    process takes ~0.1 s to produce its first line, longer than a 20-step timed region at 512^3); samples are time-stamped and
+    the ones inside [t_begin, t_end] of the timed region are used, falling back to the samples taken since the warm-up began
+    (the GPU is under the same load there) when the region was shorter than one sampling period."""
 
-    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    FIELDS = "timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index=0):
         self.gpu, self.proc, self.path = gpu_index, None, None
@@ -69,13 +74,16 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL,
             )  # fmt: skip
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """t_begin / t_end: time.time() bracketing the timed region."""
+        import datetime
+
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -83,23 +91,30 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        rows = []
         for line in open(self.path):
             parts = [s.strip() for s in line.split(",")]
-            if len(parts) < 9:
+            if len(parts) < 10:
                 continue
             try:
-                sm.append(float(parts[1]))
-                smax.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[2]), float(parts[3]), parts[6:10]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+        os.unlink(self.path)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        inside = [r for r in rows if t_begin is not None and t_begin <= r[0] <= t_end]
+        window = "timed region"
+        if not inside:
+            inside, window = rows, "warm-up + timed region (the region was shorter than one sampling period)"
+        reasons = set()
+        for r in inside:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.path)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(max(r[2] for r in inside)), "reasons": sorted(reasons),
+                "samples": len(inside), "window": window}  # fmt: skip
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -176,6 +191,83 @@ def obstacle_bcs(kind, grid, shape):
     return [FullwayBounceBackBC(indices=walls), inlet, ExtrapolationOutflowBC(indices=bne["right"]), HalfwayBounceBackBC(indices=body)]
 
 
+DTYPE_NAME = {"FP32FP32": "f32", "FP32FP16": "f32 compute / f16 store", "FP64FP32": "f64 compute / f32 store", "FP64FP64": "f64", "FP64FP16": "f64 compute / f16 store"}
+WHAT = {"cavity": "lid-driven cavity of examples/performance/mlups_3d.py", "periodic": "fully periodic box",
+        "sphere": "flow past a sphere (examples/cfd/flow_past_sphere_3d.py geometry)",
+        "tunnel": "synthetic voxelised bluff body in a wind tunnel (windtunnel_3d.py boundary set)"}  # fmt: skip
+
+
+def global_shape(args, world):
+    n = args.n
+    if args.config == "sphere":  # BASELINE C3: 1024x512x512 (= 2n x n x n)
+        return (2 * n, n, n)
+    if args.config == "tunnel":  # BASELINE C4: 1152x512x512 over 8 GPUs (= 9n/4 x n x n, rounded to the slab count)
+        return (9 * n // 4 // world * world, n, n)
+    if args.scaling == "strong":
+        return (n, n, n)
+    return (n * world, n, n)  # weak scaling: n^3 per GPU, x-slabs
+
+
+def scaling_of(args):
+    return "strong" if (args.scaling == "strong" or args.config in ("sphere", "tunnel")) else "weak"
+
+
+def config_dict(args, world, shape, omega):
+    """The `config` object of the JSON line; the native and the reference arm print the same one for the same arguments."""
+    per_gpu = f"{args.n}^3 per GPU" if scaling_of(args) == "weak" else f"{shape[0] // world}x{shape[1]}x{shape[2]} per GPU"
+    return {
+        "workload": f"{args.config} {args.lattice} {args.collision} {per_gpu} {args.policy} (global {shape[0]}x{shape[1]}x{shape[2]}); {WHAT[args.config]}",
+        "omega": omega, "n_gpus": world,
+        "l2": "inputs (2 x %.1f GB per GPU) larger than L2, no flush" % (Q[args.lattice] * STORE_BYTES[args.policy] * shape[0] * shape[1] * shape[2] / world / 1e9),
+        "parallelism": "1 GPU" if world == 1 else f"x-slab x{world}, halo fused into the face-plane kernels (peer stores over NVLink)",
+        "cells_per_thread": args.cells_per_thread or "default",
+    }  # fmt: skip
+
+
+def roofline_of(args, shape, world, ms_per_step):
+    """Roofline of the dominant kernel: ONE fused-step launch per step covers the slab (the interior launch on slab grids)."""
+    bytes_per_cell = 2 * Q[args.lattice] * STORE_BYTES[args.policy] + 1
+    cells_local = shape[0] * shape[1] * shape[2] // world
+    peak, peak_src = peaks()
+    achieved = bytes_per_cell * cells_local / (ms_per_step * 1e-3) / 1e9
+    out = {
+        "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+        "traffic": None, "bytes_per_cell": bytes_per_cell, "bytes_per_launch": bytes_per_cell * cells_local, "peak_source": peak_src,
+        "kernel": "xlbn::step_kernel", "launch_ms": round(ms_per_step, 4),
+    }  # fmt: skip
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):  # ncu --set full captures, keyed by the complete workload (config, lattice, collision, policy, local extents)
+        try:
+            key = f"{args.config}_{args.lattice}_{args.collision}_{args.policy}_{shape[0] // world}x{shape[1]}x{shape[2]}"
+            entry = json.load(open(traffic_file)).get(key)
+            if entry is not None:
+                out["traffic"] = entry["bytes"] if isinstance(entry, dict) else entry
+                if isinstance(entry, dict):
+                    out["traffic_source"] = entry.get("source")
+        except Exception:
+            pass
+    return out
+
+
+def timed_steps(torch, stepper, fields, omega, steps, warmup, barrier, t0=0):
+    """W untimed steps, then exactly K steps between CUDA events on the current stream.  Returns (ms, fields, (t_begin, t_end))."""
+    f_0, f_1, bc_mask, missing_mask = fields
+    for i in range(warmup):
+        f_0, f_1 = stepper(f_0, f_1, bc_mask, missing_mask, omega, t0 + i)
+        f_0, f_1 = f_1, f_0
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.time()
+    start.record()
+    for i in range(steps):
+        f_0, f_1 = stepper(f_0, f_1, bc_mask, missing_mask, omega, t0 + warmup + i)
+        f_0, f_1 = f_1, f_0
+    stop.record()
+    barrier()
+    return start.elapsed_time(stop), (f_0, f_1, bc_mask, missing_mask), (w0, time.time())
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -193,68 +285,40 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    n = args.n
-    shape = (n * world, n, n)  # weak scaling: n^3 per GPU, x-slabs
-    if args.config in ("sphere", "tunnel"):  # BASELINE C3: 1024x512x512 (= 2n x n x n); C4: 1152x512x512 over 8 GPUs (= 9n/4 x n x n)
-        shape = (2 * n, n, n) if args.config == "sphere" else (9 * n // 4 // world * world, n, n)
+    shape = global_shape(args, world)
     grid, stepper = build_case(args, shape)
-    f_0, f_1, bc_mask, missing_mask = stepper.prepare_fields()
+    fields = stepper.prepare_fields()
     omega = 1.0 if args.config in ("cavity", "periodic") else 1.6
     cells_total = shape[0] * shape[1] * shape[2]
-    cells_local = cells_total // world
-
-    def loop(k, t0):
-        nonlocal f_0, f_1
-        for i in range(k):
-            f_0, f_1 = stepper(f_0, f_1, bc_mask, missing_mask, omega, t0 + i)
-            f_0, f_1 = f_1, f_0
+    warmup = max(args.warmup, 3)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    loop(max(args.warmup, 3), 0)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    start.record()
-    loop(args.steps, args.warmup)
-    stop.record()
-    barrier()
-    ms = start.elapsed_time(stop)
-    clocks = sampler.stop() if rank == 0 else None
+    ms, fields, window = timed_steps(torch, stepper, fields, omega, args.steps, warmup, barrier)
+    clocks = sampler.stop(*window) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / args.steps
     mlups = cells_total * args.steps / (ms * 1e-3) / 1e6
-    finite = bool(torch.isfinite(f_0[:, :: max(1, n // 8)]).all())
-
-    # roofline of the dominant kernel: one fused-step launch per step covers the slab (interior launch on slab grids)
-    bytes_per_cell = 2 * Q[args.lattice] * STORE_BYTES[args.policy] + 1
-    peak, peak_src = peaks()
-    achieved = bytes_per_cell * cells_local / (ms_per_step * 1e-3) / 1e9
-    roofline = {
-        "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-        "traffic": None, "bytes_per_cell": bytes_per_cell, "peak_source": peak_src, "kernel": "xlbn::step_kernel",
-        "launch_ms": round(ms_per_step, 4),
-    }  # fmt: skip
-    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_file):
-        try:
-            key = f"{args.lattice}_{args.collision}_{args.policy}_{n}"
-            roofline["traffic"] = json.load(open(traffic_file)).get(key)
-        except Exception:
-            pass
+    finite = bool(torch.isfinite(fields[0][:, :: max(1, args.n // 8)]).all())
+    roofline = roofline_of(args, shape, world, ms_per_step)
 
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, stepper, grid, (f_0, f_1, bc_mask, missing_mask), cells_total, world, barrier)
+        e2e = run_e2e(args, stepper, grid, fields, cells_total, world, barrier)
+
+    secondary = None
+    if world == 1 and not args.no_secondary and (args.config, args.lattice, args.collision, args.policy, args.n) == ("cavity", "D3Q19", "BGK", "FP32FP32", 512):
+        del fields, stepper, grid
+        secondary = run_secondary(args, barrier)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -263,25 +327,49 @@ def run_native(args):
     launches_per_step = 1 if world == 1 else 3 + 2  # interior + 2 face planes + wait + signal
     if rank == 0:
         line = {
-            "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak" if args.config in ("cavity", "periodic") else "strong", "vs_baseline": None,
-            "dtype": {"FP32FP32": "f32", "FP32FP16": "f32 compute / f16 store", "FP64FP32": "f64 compute / f32 store", "FP64FP64": "f64", "FP64FP16": "f64 compute / f16 store"}[args.policy],
-            "data": "synthetic",
-            "config": {
-                "workload": f"{args.config} {args.lattice} {args.collision} {n}^3 per GPU {args.policy} (global {shape[0]}x{shape[1]}x{shape[2]}); "
-                            + {"cavity": "lid-driven cavity of examples/performance/mlups_3d.py", "periodic": "fully periodic box",
-                               "sphere": "flow past a sphere (examples/cfd/flow_past_sphere_3d.py geometry)",
-                               "tunnel": "synthetic voxelised bluff body in a wind tunnel (windtunnel_3d.py boundary set)"}[args.config],
-                "omega": omega, "l2": "inputs (2 x %.1f GB per GPU) larger than L2, no flush" % (Q[args.lattice] * STORE_BYTES[args.policy] * cells_local / 1e9),
-                "parallelism": "1 GPU" if world == 1 else f"x-slab x{world}, halo fused into the face-plane kernels (peer stores over NVLink)",
-                "cells_per_thread": args.cells_per_thread or "default",
-            },
+            "metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": scaling_of(args), "vs_baseline": None,
+            "dtype": DTYPE_NAME[args.policy], "data": "synthetic", "config": config_dict(args, world, shape, omega),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
             "finite": finite,
         }  # fmt: skip
+        if secondary is not None:
+            line["secondary"] = secondary
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_secondary(args, barrier):
+    """The other BASELINE workloads that fit one GPU, timed the same way (20 steps each, CUDA events): so that the driver's record
+    carries more than the headline configuration.  Each entry has its own roofline against the same measured peak."""
+    import copy
+    import gc
+
+    import torch
+
+    out = []
+    for over in (dict(policy="FP32FP16"), dict(policy="FP32FP16", config="periodic"), dict(lattice="D3Q27", collision="KBC"),
+                 dict(lattice="D3Q27", collision="KBC", config="sphere"), dict(lattice="D3Q27", policy="FP32FP16")):  # fmt: skip
+        a = copy.copy(args)
+        for k, v in over.items():
+            setattr(a, k, v)
+        try:
+            gc.collect()
+            torch.cuda.empty_cache()
+            shape = global_shape(a, 1)
+            grid, stepper = build_case(a, shape)
+            fields = stepper.prepare_fields()
+            omega = 1.0 if a.config in ("cavity", "periodic") else 1.6
+            ms, fields, _ = timed_steps(torch, stepper, fields, omega, 20, 3, barrier)
+            cells = shape[0] * shape[1] * shape[2]
+            out.append({"workload": config_dict(a, 1, shape, omega)["workload"], "value": round(cells * 20 / (ms * 1e-3) / 1e6, 1), "unit": "MLUPS",
+                        "steps": 20, "warmup": 3, "ms_per_step": round(ms / 20, 4), "dtype": DTYPE_NAME[a.policy], "roofline": roofline_of(a, shape, 1, ms / 20),
+                        "finite": bool(torch.isfinite(fields[0][:, :: max(1, a.n // 8)]).all())})  # fmt: skip
+            del fields, stepper, grid
+        except Exception as e:  # a secondary workload must never cost the headline line
+            out.append({"workload": str(over), "error": f"{type(e).__name__}: {e}"[:300]})
+    return out
 
 
 def run_e2e(args, stepper, grid, fields, cells_total, world, barrier):
@@ -334,7 +422,8 @@ def run_e2e(args, stepper, grid, fields, cells_total, world, barrier):
     d2h = (h_out.numel() * h_out.element_size()) / k + h_probe.numel() * h_probe.element_size()
     return {
         "value": round(cells_total * k / (ms * 1e-3) / 1e6, 1), "unit": "MLUPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-        "steps": k, "what": "pinned-host populations+masks -> device, K steps via stepper(...), per-step probe plane D2H, final populations -> pinned host",
+        "steps": k, "bytes_are": "per rank (each of the %d ranks moves this much per step)" % world,
+        "what": "pinned-host populations+masks -> device, K steps via stepper(...), per-step probe plane D2H, final populations -> pinned host",
     }  # fmt: skip
 
 
@@ -343,77 +432,70 @@ def run_e2e(args, stepper, grid, fields, cells_total, world, barrier):
 # ---------------------------------------------------------------------------------------------------------------------
 
 
-def cpu_lbm(args, n, steps, threads):
-    """Time `steps` steps of the same workload at edge n on the CPU; returns (MLUPS, kind, cores)."""
-    sys.path.insert(0, ROOT)
-    try:
-        from oracle import lbm_c
+def cpu_runner(args, n, threads):
+    """The oracle's C/OpenMP restatement of the reference step on the same workload at edge n, ready to be stepped (persistent
+    host buffers: no copies inside the timed calls).  The ONLY use of oracle/ in this file besides nothing: the CPU legs."""
+    from oracle import lbm_c
 
-        if lbm_c.available():
-            mlups = lbm_c.time_cavity(args.lattice, args.collision, args.policy, n, steps, threads, periodic=(args.config == "periodic"))
-            return mlups, "port", threads
-    except ImportError:
-        pass
-    from oracle import lbm_numpy as O
-
-    lat = O.Lattice(args.lattice)
-    shape = (n, n, n)
-    bcs = []
-    if args.config == "cavity":
-        box, box_ne = O.bounding_box_indices(shape), O.bounding_box_indices(shape, remove_edges=True)
-        walls = np.unique(np.concatenate([box[k] for k in ("bottom", "left", "right", "front", "back")], axis=1), axis=-1)
-        bcs = [O.BC("equilibrium", 1, box_ne["top"], rho=1.0, u=(0.02, 0.0, 0.0)), O.BC("fullway", 2, walls)]
-        bc_mask, missing = O.build_masks(bcs, shape, lat, flavor="warp")
-    else:
-        bc_mask, missing = np.zeros((1,) + shape, np.uint8), np.zeros((lat.q,) + shape, bool)
-    f = O.initialize_eq(shape, lat, args.policy)
-    f = O.run(f, bc_mask, missing, bcs, 1.0, lat, 1, policy=args.policy, collision=args.collision)
-    t0 = time.perf_counter()
-    O.run(f, bc_mask, missing, bcs, 1.0, lat, steps, policy=args.policy, collision=args.collision)
-    dt = time.perf_counter() - t0
-    return n**3 * steps / dt / 1e6, "port", 1
+    if not lbm_c.available():
+        raise RuntimeError("oracle/liblbm_ref.so is not built (python -c 'import __graft_entry__ as g; g.build()')")
+    return lbm_c.cavity_runner(args.lattice, args.collision, args.policy, n, threads, periodic=(args.config == "periodic"))
 
 
 def cpu_baseline(args):
+    """Bounded sample for the native arm's line: the same workload at 128^3, 3 x 10 steps after a warm-up step, all host threads."""
     threads = os.cpu_count() or 1
-    n, steps = 128, 10
-    mlups, kind, cores = cpu_lbm(args, n, steps, threads)
+    n, steps, reps = 128, 10, 3
+    r = cpu_runner(args, n, threads)
+    r.steps(1)
+    vals = [n**3 * steps / r.steps(steps) / 1e6 for _ in range(reps)]
     return {
-        "value": round(mlups, 2), "unit": "MLUPS", "cores": cores, "kind": kind,
-        "sample": f"{args.config} {args.lattice} {args.collision} {args.policy} at {n}^3 for {steps} steps (bounded sample of the 512^3 workload; "
-                  "CPU restatement of the reference's step, the reference itself needs jax/warp which are not installed)",
+        "value": round(float(np.mean(vals)), 2), "unit": "MLUPS", "cores": threads, "kind": "port",
+        "sample": f"{args.config} {args.lattice} {args.collision} {args.policy} at {n}^3, mean of {reps} x {steps} steps (bounded sample of the 512^3 workload; the "
+                  "reference arm, bench.py --impl reference, times the full-size grid; CPU restatement of the reference's step — the reference itself needs jax / warp, not installed)",
     }  # fmt: skip
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU path for the SAME configuration (512^3 by default: 22 GB of host memory), one LBM step per
+    bench step, all host threads.  jax / warp are not installable here, so the stepping code is the oracle's C/OpenMP
+    restatement of the reference's fused Warp kernel, which reproduces the reference's own WARP backend bit for bit
+    (tests/test_warp_path_golden.py).  Stops after ~200 s of stepping and reports the steps it completed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.config not in ("cavity", "periodic"):
+        raise SystemExit("--impl reference: cavity / periodic workloads")
     threads = os.cpu_count() or 1
-    n = 128
-    per_step = 4  # LBM steps per bench "step": a bounded sample of the workload
-    cpu_lbm(args, n, 1, threads)
-    t0 = time.perf_counter()
-    vals = []
-    for _ in range(max(1, args.warmup)):
-        cpu_lbm(args, n, 1, threads)
-    t0 = time.perf_counter()
+    world = args.gpus
+    shape = global_shape(args, world)
+    n = args.n
+    try:
+        r = cpu_runner(args, n, threads)
+        sample = f"the full {n}^3 grid of one rank, 1 LBM step per bench step"
+    except MemoryError:
+        n = 256
+        r = cpu_runner(args, n, threads)
+        sample = f"{n}^3 (the host could not hold the full {args.n}^3 grid), 1 LBM step per bench step"
+    budget, t_all = 200.0, time.perf_counter()
+    for _ in range(min(max(args.warmup, 1), 2)):
+        r.steps(1)
+    times = []
     for _ in range(args.steps):
-        v, kind, cores = cpu_lbm(args, n, per_step, threads)
-        vals.append(v)
-        if time.perf_counter() - t0 > 150:
+        times.append(r.steps(1))
+        if time.perf_counter() - t_all > budget:
             break
-    elapsed = time.perf_counter() - t0
-    value = float(np.mean(vals))
-    sample = f"{args.config} {args.lattice} {args.collision} {args.policy} at {n}^3, {per_step} LBM steps per bench step, {len(vals)} bench steps"
+    value = n**3 * len(times) / sum(times) / 1e6
+    if len(times) < args.steps:
+        sample += f"; stopped after {len(times)} of {args.steps} steps ({budget:.0f} s budget)"
     line = {
-        "impl": "reference", "metric": "MLUPS", "value": round(value, 2), "unit": "MLUPS", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
-        "ms_per_step": round(elapsed / max(1, len(vals)) * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config} {args.lattice} {args.collision} 512^3 {args.policy} (timed on a bounded {n}^3 sample)"},
-        "cpu_baseline": {"value": round(value, 2), "unit": "MLUPS", "cores": cores, "kind": kind, "sample": sample},
+        "impl": "reference", "metric": "MLUPS", "value": round(value, 2), "unit": "MLUPS", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+        "ms_per_step": round(sum(times) / len(times) * 1e3, 2), "higher_is_better": True, "scaling": scaling_of(args), "vs_baseline": None,
+        "dtype": DTYPE_NAME[args.policy], "data": "synthetic", "config": config_dict(args, world, shape, 1.0),
+        "cpu_baseline": {"value": round(value, 2), "unit": "MLUPS", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 2), "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference's CPU path: jax / warp are not installed in this image, so this is the oracle's restatement of the reference's step on the host cores",
+        "note": "reference's CPU path: jax / warp are not installed in this image, so this is the oracle's C/OpenMP restatement of the reference's fused step "
+                "(bit-identical to the reference's WARP backend on the test vectors) on the host cores; one rank's grid, N ranks would each do the same",
     }  # fmt: skip
     print(json.dumps(line))
 

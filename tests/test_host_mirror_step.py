@@ -226,3 +226,23 @@ def test_cells_per_thread_variants_are_identical_to_one_cell_per_thread(mirror, 
     if g["shape"][-1] % v:
         pytest.skip("nz not divisible")
     assert np.array_equal(mirror_run(mirror, g, steps=8, v=v), mirror_run(mirror, g, steps=8, v=1))
+
+
+BGK_F32 = [n for n in STEP_CASES + LATE_CASES + WARP_CASES + WARP_CASES_FP16 if "bgk" in n]  # every policy, fp64 compute included
+
+
+@pytest.mark.parametrize("name", BGK_F32)
+def test_bgk_source_is_bit_identical_to_the_reference_kernel(mirror, name):
+    """The BGK chain of the kernel source (macroscopic -> equilibrium -> BGK, every BC functional) takes one IEEE rounding per operation in
+    the reference's operation order (csrc/lbm_math.cuh "ROUNDINGS"; the library is built with -fmad=false), so fp32-compute runs — fp32
+    or fp16 storage — reproduce the C restatement of the reference's fused Warp kernel BIT FOR BIT, on the scalar path and on the
+    half2-state pair path (whose packed arithmetic and shared-reciprocal division round identically)."""
+    from common import c_oracle_run
+
+    g = load_golden(name)
+    ref, _, _ = c_oracle_run(g)
+    f = mirror_run(mirror, g)
+    assert np.array_equal(f, ref), f"scalar path: rel err {rel_err(f, ref):.3e}, {int((f != ref).sum())} values differ"
+    if g["policy"] == "FP32FP16" and g["shape"][-1] % 2 == 0 and len(g["shape"]) == 3:
+        f2 = mirror_run(mirror, g, v=202)
+        assert np.array_equal(f2, ref), f"half2-state path: rel err {rel_err(f2, ref):.3e}, {int((f2 != ref).sum())} values differ"

@@ -26,9 +26,10 @@ def test_reference_arm_prints_contract_line():
 
     if not lbm_c.available():
         pytest.skip("oracle/liblbm_ref.so not built")
-    proc = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1"], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    proc = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "2", "--warmup", "1", "--n", "64"], cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert proc.returncode == 0, proc.stderr
     line = json.loads(proc.stdout.strip().splitlines()[-1])
+    assert line["steps"] == 2 and "cavity D3Q19 BGK 64^3 per GPU FP32FP32" in line["config"]["workload"] and line["scaling"] == "weak"
     assert line["impl"] == "reference" and line["metric"] == "MLUPS" and line["unit"] == "MLUPS" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -35,10 +35,14 @@ XLBN_DEV void macroscopic(const TC (&f)[L::Q], TC& rho, TC (&u)[L::D]) {
 
 // feq_l = rho w_l (1 + cu (1 + 0.5 cu) - usqr), cu = 3 c_l.u, usqr = 1.5 u.u
 // (reference: quadratic_equilibrium.py:35-60)
+// ROUNDINGS.  The library is compiled with -fmad=false: the compiler never contracts a*b+c, every fused operation is an explicit
+// fma_() in the source.  The BGK chain (macroscopic -> equilibrium -> BGK, and the BC functionals) uses NONE: one IEEE rounding per
+// operation, in the reference's operation order — exactly what the reference's functionals evaluate — so that fp32 results are
+// bit-identical to the reference kernel as restated by oracle/lbm_ref.c, and fp16 storage sees the same roundings step after step.
 template <class L, class TC>
 XLBN_DEV void equilibrium(TC rho, const TC (&u)[L::D], TC (&feq)[L::Q]) {
   TC uu = u[0] * u[0];
-  XLBN_FOR(L::D - 1, d) uu = fma_(u[d + 1], u[d + 1], uu); XLBN_END
+  XLBN_FOR(L::D - 1, d) uu = uu + u[d + 1] * u[d + 1]; XLBN_END
   const TC usqr = TC(1.5) * uu;
   XLBN_FOR(L::Q, l)
     TC cu = TC(0);
@@ -47,8 +51,7 @@ XLBN_DEV void equilibrium(TC rho, const TC (&u)[L::D], TC (&feq)[L::Q]) {
       else if constexpr (L::c(d, l) == -1) cu -= u[d];
     XLBN_END
     cu *= TC(3.0);
-    // 1 + cu (1 + cu/2) - usqr with the two contractions written out (same result for every compute type)
-    feq[l] = rho * TC(L::w(l)) * (fma_(cu, fma_(TC(0.5), cu, TC(1.0)), TC(1.0)) - usqr);
+    feq[l] = rho * TC(L::w(l)) * (TC(1.0) + cu * (TC(1.0) + TC(0.5) * cu) - usqr);  // quadratic_equilibrium.py:58, one rounding per operation
   XLBN_END
 }
 
@@ -69,7 +72,7 @@ template <class L, class TC>
 XLBN_DEV void collide_bgk(const TC (&f)[L::Q], const TC (&feq)[L::Q], TC omega, TC (&out)[L::Q]) {
   XLBN_FOR(L::Q, l)
     const TC fneq = f[l] - feq[l];
-    out[l] = fma_(-omega, fneq, f[l]);
+    out[l] = f[l] - omega * fneq;  // bgk.py:33, unfused
   XLBN_END
 }
 

@@ -606,10 +606,11 @@ XLBN_DEV void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L
       else if constexpr (L::c(d, l) == -1) u[d] -= f;
     XLBN_END
   XLBN_END
-  const f32x2 inv = rcp_(rho);
-  XLBN_FOR(L::D, d) u[d] = u[d] * inv; XLBN_END
+  // u = (sum c f) / rho, correctly rounded (first_moment.py:38); every operation below is one IEEE rounding in the reference's order
+  const f32x2 inv = rcp_refined_(rho);
+  XLBN_FOR(L::D, d) u[d] = div_by_(u[d], rho, inv); XLBN_END
   f32x2 uu = u[0] * u[0];
-  XLBN_FOR(L::D - 1, d) uu = fma_(u[d + 1], u[d + 1], uu); XLBN_END
+  XLBN_FOR(L::D - 1, d) uu = uu + u[d + 1] * u[d + 1]; XLBN_END
   const f32x2 usqr = f32x2(1.5f) * uu;
   const f32x2 omega((float)p.omega);
   // equilibrium + BGK relaxation per population (quadratic_equilibrium.py:35-60, bgk.py:30-34), narrowed and stored at once
@@ -621,8 +622,8 @@ XLBN_DEV void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L
       else if constexpr (L::c(d, l) == -1) cu -= u[d];
     XLBN_END
     cu *= f32x2(3.0f);
-    const f32x2 feq = rho * f32x2(L::w(l)) * (fma_(cu, fma_(f32x2(0.5f), cu, f32x2(1.0f)), f32x2(1.0f)) - usqr);
-    f32x2 out = fma_(-omega, f - feq, f);
+    const f32x2 feq = rho * f32x2(L::w(l)) * (f32x2(1.0f) + cu * (f32x2(1.0f) + f32x2(0.5f) * cu) - usqr);
+    f32x2 out = f - omega * (f - feq);
     if constexpr (BCV == 2) {  // bc_equilibrium.py:76-86 followed by the ordinary collision = a per-BC constant
       if (eq_lo) out.v.x = out_lo[l];
       if (eq_hi) out.v.y = out_hi[l];
@@ -650,58 +651,8 @@ XLBN_DEV void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L
 // relaxation, whose result is narrowed (one F2FP) and stored immediately.  Live state: q + ~25 registers for two cells,
 // so the kernel keeps the residency of the one-cell path while issuing ~2.5x fewer instructions per cell (FADD2 / FMUL2 /
 // FFMA2 for both cells at once); the fp16 path is issue-bound otherwise (profiles/README.md).
-//
-// Boundary cells (round 2): z is the thread axis, so in a closed box the floor / lid cells sit in ONE lane of the first and
-// last warp of EVERY row — with two cells per thread a quarter of all warps.  Round 1 sent those whole warps through a
-// boundary variant of the collide-store routine that spilled (ncu: 55 M spill instructions, DRAM writes 1.21 x algorithmic,
-// cavity 0.71 vs periodic 0.84 of the roofline).  Now every thread whose two cells are fluid / FullwayBounceBack /
-// EquilibriumBC runs the SAME straight-line code (both halves treated as fluid), and only the lanes that own a boundary
-// cell overwrite that half afterwards with 2-byte stores: the opposite population's half (Fullway: bit copy,
-// bc_fullway_bounce_back.py:60-72) or the precomputed constant update (EquilibriumBC + collision, BcEntry::eq_out).  Same
-// thread, same address, program order: the patch lands after the pair store.  Threads with any other kind (or a 255 cell)
-// take the scalar boundary tail as before.  SPLIT (cells_per_thread = 203) is kept as an alias of the same code.
-// Out of line on purpose: called by the few lanes that own a FullwayBounceBack / EquilibriumBC cell, AFTER the pair store.  It keeps
-// nothing of the caller alive (the post-stream values are re-read, L1 / L2 hits), so the straight-line code is allocated as if the
-// boundary did not exist.
-template <class L, int XC>
-XLBN_DEVFN __noinline__ void h2_patch(const StepParams<__half>& p, const int x, const int y, const int z0) {
-  using TS = __half;
-  const unsigned nz = (unsigned)p.nz;
-  const unsigned xoff = (unsigned)x * (unsigned)p.plane;
-  const unsigned row_c = xoff + (unsigned)y * nz;
-  const unsigned row_m = xoff + (unsigned)(y == 0 ? p.ny - 1 : y - 1) * nz;
-  const unsigned row_p = xoff + (unsigned)(y == p.ny - 1 ? 0 : y + 1) * nz;
-#pragma unroll 1
-  for (int v = 0; v < 2; ++v) {
-    const unsigned z = (unsigned)z0 + (unsigned)v;
-    const unsigned cell = row_c + z;
-    const int id = p.bc[cell];
-    if (id == 0) continue;
-    const bool eq = p.kinds[id] == XLBN_BC_EQUILIBRIUM;
-    const float* out = p.table[id].eq_out;
-    const unsigned z_m = (z == 0) ? nz - 1 : z - 1;   // source of c_z = +1 populations
-    const unsigned z_p = (z + 1 >= nz) ? 0u : z + 1;  // source of c_z = -1 populations
-    XLBN_FOR(L::Q, l)
-      Pack<TS, 1> a;
-      if (eq) {  // bc_equilibrium.py:76-86 followed by the ordinary collision = a per-BC constant (bc_precompute_kernel)
-        a.v[0] = __float2half_rn(out[l]);
-      } else {  // bc_fullway_bounce_back.py:60-72: out[l] = f_post_stream[opp l] = the pulled value of population opp(l); a bit copy
-        constexpr int o = L::opp(l);
-        constexpr int cx = L::ck(0, o), cy = L::ck(1, o), cz = L::ck(2, o);
-        constexpr int tab = (cx == 1 && (XC & 1)) ? 1 : ((cx == -1 && (XC & 2)) ? 2 : 0);
-        const unsigned row = (cy == 1 ? row_m : (cy == -1 ? row_p : row_c));
-        a = gload<TS, 1>(p.pull[tab][o] + (row + (cz == 1 ? z_m : (cz == -1 ? z_p : z))));
-      }
-      gstore<TS, 1>(p.push[l] + cell, a);
-      if constexpr (L::ck(0, l) == 1 && (XC & 2)) {
-        if (p.peer_hi[l]) gstore<TS, 1>(p.peer_hi[l] + cell, a);
-      } else if constexpr (L::ck(0, l) == -1 && (XC & 1)) {
-        if (p.peer_lo[l]) gstore<TS, 1>(p.peer_lo[l] + cell, a);
-      }
-    XLBN_END
-  }
-}
-
+// SPLIT (tuning variant, cells_per_thread = 203): warps whose boundary cells are all FullwayBounceBack take a leaner boundary
+// variant without the EquilibriumBC table pointers / constant loads.
 template <class L, int XC, bool SPLIT = false>
 XLBN_DEV void step_body_h2(const StepParams<__half>& p, const int x, const int y, const int z0) {
   using TS = __half;
@@ -720,8 +671,8 @@ XLBN_DEV void step_body_h2(const StepParams<__half>& p, const int x, const int y
   const bool any_bc = (ids.v[0] != 0) | (ids.v[1] != 0);
   if ((ids.v[0] == 255) & (ids.v[1] == 255)) return;
 
-  // Two copies of the load phase (the branch is taken BEFORE anything is loaded), so that the register allocation of the
-  // straight-line path is independent of the scalar boundary tail.
+  // Three separate code paths, each with its own load phase, so that the register allocation of the straight-line path
+  // is independent of the boundary code (the branch is taken BEFORE anything is loaded).
   auto load_all = [&](__half2 (&h)[Q]) {
     XLBN_FOR(Q, l)
       constexpr int cx = L::ck(0, l), cy = L::ck(1, l), cz = L::ck(2, l);
@@ -741,29 +692,50 @@ XLBN_DEV void step_body_h2(const StepParams<__half>& p, const int x, const int y
     XLBN_END
   };
 
-  if (any_bc) {
-    const int k0 = ids.v[0] ? (int)p.kinds[ids.v[0]] : 0, k1 = ids.v[1] ? (int)p.kinds[ids.v[1]] : 0;
-    const auto simple = [](int id, int k) { return id != 255 && (k == XLBN_BC_NONE || k == XLBN_BC_FULLWAY_BOUNCE_BACK || k == XLBN_BC_EQUILIBRIUM); };
-    if (!(simple(ids.v[0], k0) && simple(ids.v[1], k1))) {
-      // other kinds / solid cells: widen and take the scalar boundary tail
-      __half2 h[Q];
-      load_all(h);
-      float fs[V][Q];
-      XLBN_FOR(Q, l)
-        const float2 f = __half22float2(h[l]);
-        fs[0][l] = f.x;
-        fs[1][l] = f.y;
-      XLBN_END
-      bc_tail<L, XLBN_BGK, float, TS, V, XC>(p, ids, x, y, z0, cell, any_solid, fs);
-      return;
-    }
-  }
-  {
+  // Warp-uniform choice of the code path (threads of a warp never serialise through two paths):
+  //   no boundary cell in the warp                      -> straight pair path
+  //   only fluid / FullwayBounceBack / EquilibriumBC    -> pair path with per-half boundary handling
+  //   anything else (other BC kinds, solid cells)       -> per-thread: pair path or scalar boundary tail
+  const int k0 = ids.v[0] ? (int)p.kinds[ids.v[0]] : 0, k1 = ids.v[1] ? (int)p.kinds[ids.v[1]] : 0;
+  const auto simple = [](int id, int k) { return id != 255 && (k == XLBN_BC_NONE || k == XLBN_BC_FULLWAY_BOUNCE_BACK || k == XLBN_BC_EQUILIBRIUM); };
+  const unsigned active = XLBN_ACTIVEMASK();
+  const bool warp_any_bc = XLBN_ANY(active, any_bc);
+  if (!warp_any_bc) {
     __half2 h[Q];
     load_all(h);
     h2_collide_store<L, XC, 0>(p, h, cell, 0, 0);
+    return;
   }
-  if (any_bc) h2_patch<L, XC>(p, x, y, z0);  // one lane of the first / last warp of a row in a closed box; whole warps on wall rows / planes
+  if (XLBN_ALL(active, simple(ids.v[0], k0) && simple(ids.v[1], k1))) {
+    if constexpr (SPLIT) {
+      if (XLBN_ALL(active, k0 != XLBN_BC_EQUILIBRIUM && k1 != XLBN_BC_EQUILIBRIUM)) {
+        __half2 h[Q];
+        load_all(h);
+        h2_collide_store<L, XC, 1>(p, h, cell, ids.v[0], ids.v[1]);
+        return;
+      }
+    }
+    __half2 h[Q];
+    load_all(h);
+    h2_collide_store<L, XC, 2>(p, h, cell, ids.v[0], ids.v[1]);
+    return;
+  }
+  if (!any_bc) {
+    __half2 h[Q];
+    load_all(h);
+    h2_collide_store<L, XC, 0>(p, h, cell, 0, 0);
+    return;
+  }
+  __half2 h[Q];
+  load_all(h);
+  // threads with boundary cells: widen and take the scalar boundary tail
+  float fs[V][Q];
+  XLBN_FOR(Q, l)
+    const float2 f = __half22float2(h[l]);
+    fs[0][l] = f.x;
+    fs[1][l] = f.y;
+  XLBN_END
+  bc_tail<L, XLBN_BGK, float, TS, V, XC>(p, ids, x, y, z0, cell, any_solid, fs);
 }
 
 template <class L, int COLL, class TC, class TS, int V, int MODE>

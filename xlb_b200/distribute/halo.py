@@ -77,6 +77,8 @@ class PeerHalo:
         nx, ny, nz = dims
         self.handle = C.c_void_p()
         L = native.lib()
+        if self.device.type == "cuda":
+            torch.cuda.set_device(self.device)  # the ghost block and the IPC mappings belong to the slab's device
         native.check(L.xlbn_halo_create(velocity_set.lattice_code, precision_policy.store_precision.code, ny, nz, C.byref(self.handle)))
         mine = C.create_string_buffer(64)
         native.check(L.xlbn_halo_export(self.handle, mine))
@@ -97,17 +99,13 @@ class PeerHalo:
             pass
 
     def timed_out(self) -> bool:
-        """True if a device-side wait for the neighbours' step counters ever gave up (10 s; the wait kernel then sets a
-        marker instead of hanging the GPU).  Synchronises the device; call it outside the stepping loop."""
-        base, nbytes = C.c_void_p(), C.c_longlong()
-        native.check(native.lib().xlbn_halo_ghost_ptr(self.handle, C.byref(base), C.byref(nbytes)))
+        """True once a device-side wait for the neighbours' step counters gave up (default 120 s, `set_timeout` / environment
+        XLBN_HALO_TIMEOUT_S).  The wait kernel never hangs the GPU: it marks the handle in mapped host memory, and from then on
+        every `step` raises (XLBN_E_STATE): the step that timed out read stale ghosts.  No device synchronisation."""
+        return native.lib().xlbn_halo_timed_out(self.handle) == 1
 
-        class _Flags:  # the last 256 bytes of the ghost block hold int flags[4]; flags[2] is the timeout marker
-            __cuda_array_interface__ = {"shape": (4,), "typestr": "<i4", "data": (base.value + nbytes.value - 256, True), "version": 2}
-
-        torch.cuda.synchronize(self.device)
-        flags = torch.as_tensor(_Flags(), device=self.device).cpu()
-        return bool(flags[2].item() != 0)
+    def set_timeout(self, seconds: float):
+        native.check(native.lib().xlbn_halo_set_timeout(self.handle, float(seconds)))
 
     def step(self, stepper_handle, f_0, f_1, bc_mask, bits, dims, omega, t):
         L = native.lib()
@@ -122,6 +120,9 @@ class PeerHalo:
             native.check(L.xlbn_halo_signal(self.handle, t, main_p))
             self.primed = True
         args = (stepper_handle, native.ptr(f_0), native.ptr(f_1), native.ptr(bc_mask), native.ptr(bits))
+        if omega != getattr(self, "_omega", None):  # one step = launches on two streams: publish omega on the one both are ordered after
+            native.check(L.xlbn_stepper_prepare(stepper_handle, omega, main_p))
+            self._omega = omega
         if nx < 3:  # nothing to overlap
             native.check(L.xlbn_halo_wait(self.handle, t, main_p))
             native.check(L.xlbn_step(*args, C.byref(full), omega, t, self.handle, main_p))

@@ -54,6 +54,10 @@ class Grid:
             raise ValueError(f"grid must be 2-D or 3-D, got shape {shape}")
         self.compute_backend = compute_backend or DefaultConfig.default_backend or ComputeBackend.WARP
         self.device = torch.device(device) if device is not None else default_device()
+        if self.device.type == "cuda" and _dist_state()[1] > 1:
+            # one process per GPU: the native library allocates (BC table, ghost planes) and launches on the CURRENT device, and a
+            # reference-style script never calls torch.cuda.set_device itself
+            torch.cuda.set_device(self.device)
 
         rank, world = _dist_state() if distributed is None else distributed
         self.rank, self.nDevices = int(rank), int(world)

@@ -133,7 +133,11 @@ class IncompressibleNavierStokesStepper(Stepper):
         return f_0, f_1
 
     # -- native handle ---------------------------------------------------------------------------------------------------
-    def _native_handle(self):
+    def _native_handle(self, device=None):
+        """The native stepper (device BC table); created on `device` — the populations' device, not whatever is current."""
+        if device is not None and device.type == "cuda" and torch.cuda.current_device() != device.index:
+            with torch.cuda.device(device):
+                return self._native_handle()
         descs = [bc.native_desc() for bc in self.boundary_conditions]
         coll = self.collision.native_collision
         force = self.collision.native_force
@@ -156,6 +160,7 @@ class IncompressibleNavierStokesStepper(Stepper):
         out = C.c_void_p()
         native.check(native.lib().xlbn_stepper_create(C.byref(desc), C.byref(out)))
         self._handle, self._handle_key = out, key
+        self._graph = self._graph_key = None  # a captured graph holds the old handle's device table
         if coll & ~native.COLLISION_FORCED == native.SMAGORINSKY_LES_BGK:
             native.check(native.lib().xlbn_stepper_set_smagorinsky(out, float(self.collision.native_smagorinsky)))
         if force is not None:
@@ -188,7 +193,7 @@ class IncompressibleNavierStokesStepper(Stepper):
         if bc_mask.dtype != torch.uint8 or bc_mask.shape[1:] != f_0.shape[1:]:
             raise ValueError("bc_mask must be uint8 [1, ...] matching the populations")
         nx, ny, nz = native.dims_of(f_0, vs.d)
-        handle = self._native_handle()
+        handle = self._native_handle(f_0.device)
         bits = self._missing_bits(missing_mask) if self._needs_missing else None
         if self.grid is not None and self.grid.nDevices > 1:
             return self._step_slab(handle, f_0, f_1, bc_mask, bits, (nx, ny, nz), float(omega))
@@ -226,17 +231,22 @@ class IncompressibleNavierStokesStepper(Stepper):
             return f_0, f_1
         pairs = n_steps // 2
         if use_graph and pairs >= 2:
-            key = (f_0.data_ptr(), f_1.data_ptr(), bc_mask.data_ptr(), missing_mask.data_ptr(), missing_mask._version, float(omega), tuple(f_0.shape))
-            if getattr(self, "_graph_key", None) != key:
-                # two plain steps first: handle creation, bitmask packing and the EquilibriumBC constants (which synchronise) must
-                # not happen inside a capture
+            # two plain steps first: handle creation and bitmask packing (allocations, host copies) must not happen inside a capture
+            self._native_handle(f_0.device)
+            key = (f_0.data_ptr(), f_1.data_ptr(), bc_mask.data_ptr(), bc_mask._version, missing_mask.data_ptr(), missing_mask._version, float(omega),
+                   tuple(f_0.shape), self._handle_key, self._handle.value)  # fmt: skip
+            if getattr(self, "_graph_key", None) != key or getattr(self, "_graph_bits", None) is not self._bits:
                 self._step(f_0, f_1, bc_mask, missing_mask, omega, timestep)
                 self._step(f_1, f_0, bc_mask, missing_mask, omega, timestep + 1)
                 pairs -= 1
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
+                    # the per-omega constants are (re)published INSIDE the graph, so a replay never depends on which omega the
+                    # stepper saw last outside it
+                    native.check(native.lib().xlbn_stepper_prepare(self._handle, float(omega), native.stream_of(f_0)))
                     self._step(f_0, f_1, bc_mask, missing_mask, omega, timestep)
                     self._step(f_1, f_0, bc_mask, missing_mask, omega, timestep + 1)
+                self._graph_bits = self._bits
                 pairs -= 1  # the capture pass above does not execute; replay it once for the pair it stands for
                 graph.replay()
                 self._graph, self._graph_key = graph, key
