@@ -168,12 +168,14 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
  * global coordinate of local cell (0,0,0) (slab decomposition; = local dims and {0,0,0} on one GPU).
  * XLBN_MASK_JAX additionally needs a zero-initialised uint8 scratch `solid` of the local extents plus one halo cell on
  * every side, i.e. (nx+2)(ny+2)(nz+2) bytes (nz+2 -> 1 in 2-D is NOT applied: pass nz = 1 and the library pads it),
- * and a final xlbn_mask_finalize_jax call after the last BC. */
+ * and a final xlbn_mask_finalize_jax call after the last BC; entries that were already set in the caller's missing mask are streamed
+ * like the reference does (L56-63, 92) when a copy of that mask is passed as `incoming`. */
 int xlbn_mask_indices(int lattice, int mode, const int32_t* indices, long long n, int bc_id, int needs_padding,
                       const int32_t global_dims[3], const int32_t start[3], const int32_t local_dims[3],
                       uint8_t* bc_mask, uint8_t* missing /* bool [q][nx][ny][nz] */, uint8_t* solid, void* stream);
 int xlbn_mask_finalize_jax(int lattice, const int32_t global_dims[3], const int32_t start[3], const int32_t local_dims[3],
-                           uint8_t* missing, const uint8_t* solid, void* stream);
+                           uint8_t* missing, const uint8_t* solid, const uint8_t* incoming /* copy of the caller's mask, or NULL if it was all false */,
+                           void* stream);
 
 /* Replaces MeshBoundaryMasker.warp_implementation (mesh_boundary_masker.py:49-236; 3-D only) for ONE mesh-based BC: surface
  * voxelisation of a triangle soup.  vertices: device float32 [n_triangles][3 vertices][3], grid units, the whole mesh inside

@@ -78,8 +78,56 @@ int host_step_pair(const StepCall& c) {
   return 0;
 }
 
+// The tile kernel (csrc/step_tile.cuh; cells_per_thread 402) with its asynchronous machinery replaced by what it amounts to: the
+// producer's copy plan executed with memcpy into an input stage, the 256 consumer threads of the tile run one after the other
+// (tile_load + tile_compute: the shipped per-thread code, which stores to the destination itself).
+template <class L>
+int host_step_tile(const StepCall& c) {
+  StepParams<__half> p;
+  if (int e = fill_step_params<L, __half>(c, p)) return e;
+  if (!tile_eligible<L>(p, c.f0, c.f1, c.ghost_lo, c.ghost_hi, c.out_lo != nullptr || c.out_hi != nullptr)) return fail(XLBN_E_SHAPE, "mirror: shape not eligible for the tile kernel");
+  BcEntry* table = c.table_rw;  // bc_precompute_kernel
+  for (int id = 0; id < 256; ++id) {
+    if (table[id].kind != XLBN_BC_EQUILIBRIUM) continue;
+    float u[L::D], f[L::Q];
+    XLBN_FOR(L::D, d) u[d] = (float)table[id].u[d]; XLBN_END
+    equilibrium<L, float>((float)table[id].rho, u, f);
+    collide_cell<L, XLBN_BGK, float, false>(f, (float)c.omega);
+    XLBN_FOR(L::Q, l) table[id].eq_out[l] = f[l]; XLBN_END
+  }
+  using C = TileCfg<L, 2>;
+  const int rows = kTileCells / p.nz, tiles_per_plane = p.ny / rows, n_tiles = tiles_per_plane * c.x_count;
+  static unsigned char in[C::kInBytes];
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const TileGeom g = tile_geom(p, tile, rows, tiles_per_plane);
+    memset(in, 0xff, sizeof(in));
+    for (int l = 0; l < L::Q; ++l) {  // the producer warp, lane l
+      const __half* src[2];
+      unsigned dst[2], count[2];
+      const int n = tile_plan<L>(p, l, g, rows, src, dst, count);
+      unsigned total = 0;
+      for (int i = 0; i < n; ++i) {
+        if ((reinterpret_cast<uintptr_t>(src[i]) % 16) || ((dst[i] * 2u) % 16) || ((count[i] * 2u) % 16)) return fail(XLBN_E_SHAPE, "mirror: bulk copy not 16-byte aligned");
+        memcpy(in + l * kTileRowBytes + dst[i] * 2u, src[i], count[i] * 2u);
+        total += count[i];
+      }
+      if (total != (unsigned)kTileCells) return fail(XLBN_E_SHAPE, "mirror: copy plan covers %u of 512 elements", total);
+    }
+    memcpy(in + L::Q * kTileRowBytes, p.bc + g.cell0, kTileCells);
+    for (unsigned t = 0; t < (unsigned)kTileConsumers; ++t) {  // the consumer threads
+      __half2 h[L::Q];
+      unsigned ids;
+      tile_load<L>(p, reinterpret_cast<const uint32_t*>(in), in + L::Q * kTileRowBytes, t, h, ids);
+      tile_compute<L>(p, h, ids, t, g);
+    }
+  }
+  return 0;
+}
+
 template <class L, int COLL, class TC, class TS>
 int host_step_v(const StepCall& c) {
+  if constexpr (COLL == XLBN_BGK && sizeof(TC) == 4 && sizeof(TS) == 2 && L::D == 3)
+    if (c.requested_v == 402) return host_step_tile<L>(c);
   if (c.requested_v == 1) return host_step<L, COLL, TC, TS, 1>(c);
   if constexpr (!kExtCollision<COLL> && sizeof(TC) == 4) {
     if (c.requested_v == 102) return host_step_pair<L, COLL, TS, 1>(c);

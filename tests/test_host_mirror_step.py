@@ -15,7 +15,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from common import LATE_CASES, RTOL, STEP_CASES, WARP_CASES, WARP_CASES_FP16, WARP_CASES_N4, load_golden, oracle_masks, rel_err
+from common import LATE_CASES, RTOL, STEP_CASES, WARP_CASES, WARP_CASES_FP16, WARP_CASES_N4, load_golden, oracle_masks, rel_err, tile_case
 from oracle import lbm_c
 from oracle import lbm_numpy as O
 
@@ -29,7 +29,8 @@ COLLISION = {"BGK": 0, "KBC": 1, "SmagorinskyLESBGK": 2}
 DTYPE = {np.dtype(np.float16): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}
 # (lattice, collision code) pairs the library instantiates: base | 4 = forced (XLBN_COLLISION_FORCED), | 8 = lean KBC (kLeanKbc)
 PARTS = [("D3Q19", 0), ("D3Q19", 4), ("D3Q19", 2), ("D3Q19", 6), ("D3Q27", 0), ("D3Q27", 1), ("D3Q27", 4), ("D3Q27", 5), ("D3Q27", 2), ("D3Q27", 6),
-         ("D3Q27", 9), ("D2Q9", 0), ("D2Q9", 1), ("D2Q9", 4), ("D2Q9", 5), ("D2Q9", 9)]  # fmt: skip
+         ("D3Q27", 9), ("D2Q9", 0), ("D2Q9", 1), ("D2Q9", 4), ("D2Q9", 5), ("D2Q9", 9), ("D2Q9X", 0), ("D2Q9X", 1)]  # fmt: skip
+SYM = lambda lat, coll: f"mirror_step_{'0x' if lat == 'D2Q9X' else LATTICE[lat]}_{coll}"  # noqa: E731
 
 
 @pytest.fixture(scope="module")
@@ -44,8 +45,8 @@ def mirror():
         jobs = [base + ["-c", os.path.join(CSRC, "error.cu"), "-o", os.path.join(build, "error.o")]]
         objs = [os.path.join(build, "error.o")]
         for i, (lat, coll) in enumerate(PARTS):  # one object per (lattice, collision), compiled in parallel
-            obj = os.path.join(build, f"mirror_step_{LATTICE[lat]}_{coll}.o")
-            flags = [f"-DMIRROR_LAT={lat}", f"-DMIRROR_TAG=XLBN_{lat}", f"-DMIRROR_COLL={coll}", f"-DMIRROR_NAME=mirror_step_{LATTICE[lat]}_{coll}"]
+            obj = os.path.join(build, SYM(lat, coll) + ".o")
+            flags = [f"-DMIRROR_LAT={lat}", f"-DMIRROR_TAG=XLBN_{lat.rstrip('X')}", f"-DMIRROR_COLL={coll}", f"-DMIRROR_NAME={SYM(lat, coll)}"]
             jobs.append(base + flags + (["-DMIRROR_DEFINE_ERROR"] if i == 0 else []) + ["-c", SRC, "-o", obj])
             objs.append(obj)
         running, pending = [], list(jobs)
@@ -61,11 +62,11 @@ def mirror():
     lib.mirror_last_error.restype = C.c_char_p
     P, I, D = C.c_void_p, C.c_int, C.c_double
     for lat, coll in PARTS:
-        getattr(lib, f"mirror_step_{LATTICE[lat]}_{coll}").argtypes = [I, I, I, I, I, P, P, P, P, P, P, P, P, I, I, D, P, D, P, P, P, P]
+        getattr(lib, SYM(lat, coll)).argtypes = [I, I, I, I, I, P, P, P, P, P, P, P, P, I, I, D, P, D, P, P, P, P]
     return lib
 
 
-def mirror_run(lib, g, steps=None, v=1, lean_kbc=False, masks=None):
+def mirror_run(lib, g, steps=None, v=1, lean_kbc=False, masks=None, slab_axes=False):
     """The user loop (step, swap) through the host-compiled kernel source; masks and aux data from the oracle helpers
     (or `masks` = (lat, bcs, bc_mask, missing) built by the caller)."""
     lat, bcs, bc_mask, missing = masks if masks is not None else oracle_masks(g, "warp")
@@ -80,13 +81,14 @@ def mirror_run(lib, g, steps=None, v=1, lean_kbc=False, masks=None):
     bits = np.ascontiguousarray(sum(missing[l].astype(np.uint32) << np.uint32(l) for l in range(lat.q)).astype(np.uint32))
     bm = np.ascontiguousarray(bc_mask[0])
     shape = g["shape"]
-    dims = (C.c_int32 * 3)(*((1,) + tuple(shape) if lat.d == 2 else tuple(shape)))
+    # 2-D: kernel extents (1, nx, ny); with slab_axes the x-slab axis order (nx, 1, ny) of csrc/lattice.cuh D2Q9X
+    dims = (C.c_int32 * 3)(*(((shape[0], 1, shape[1]) if slab_axes else (1,) + tuple(shape)) if lat.d == 2 else tuple(shape)))
     coll = COLLISION[g["collision"]] | (4 if g["force_vector"] is not None else 0) | (8 if lean_kbc else 0)  # 8: csrc/lbm_math.cuh kLeanKbc
     force = np.zeros(3)
     if g["force_vector"] is not None:
         force[: lat.d] = g["force_vector"]
     for _ in range(g["steps"] if steps is None else steps):
-        rc = getattr(lib, f"mirror_step_{LATTICE[g['lattice']]}_{coll}")(LATTICE[g["lattice"]], coll, DTYPE[np.dtype(cdt)], DTYPE[np.dtype(sdt)], v, fa.ctypes.data, fb.ctypes.data, bm.ctypes.data,
+        rc = getattr(lib, SYM(g["lattice"] + ("X" if slab_axes else ""), coll))(LATTICE[g["lattice"]], coll, DTYPE[np.dtype(cdt)], DTYPE[np.dtype(sdt)], v, fa.ctypes.data, fb.ctypes.data, bm.ctypes.data,
                              bits.ctypes.data, kind.ctypes.data, rho.ctypes.data, u.ctypes.data, C.cast(dims, C.c_void_p), 0, dims[0], g["omega"],
                              force.ctypes.data, g["smagorinsky"], None, None, None, None)  # fmt: skip
         assert rc == 0, lib.mirror_last_error().decode()
@@ -246,3 +248,62 @@ def test_bgk_source_is_bit_identical_to_the_reference_kernel(mirror, name):
     if g["policy"] == "FP32FP16" and g["shape"][-1] % 2 == 0 and len(g["shape"]) == 3:
         f2 = mirror_run(mirror, g, v=202)
         assert np.array_equal(f2, ref), f"half2-state path: rel err {rel_err(f2, ref):.3e}, {int((f2 != ref).sum())} values differ"
+
+
+@pytest.mark.parametrize("lattice,shape,walls", [("D3Q19", (3, 4, 512), True), ("D3Q19", (4, 8, 128), True), ("D3Q27", (3, 16, 64), True), ("D3Q19", (2, 64, 8), False),
+                                                 ("D3Q27", (5, 2, 256), False), ("D3Q19", (1, 32, 16), True)])  # fmt: skip
+def test_tile_kernel_logic_is_bit_identical_to_the_reference_kernel(mirror, lattice, shape, walls):
+    """cells_per_thread 402 (csrc/step_tile.cuh): copy plan (y wrap, x wrap), z rotation inside the stage rows, boundary handling in the
+    output stage — executed on the host with the bulk copies as memcpy — against the C oracle, bit for bit."""
+    from common import c_oracle_run
+
+    g = tile_case(lattice, shape, 6, 11, walls)
+    ref, _, _ = c_oracle_run(g)
+    f = mirror_run(mirror, g, v=402)
+    assert np.array_equal(f, ref), f"{int((f != ref).sum())} of {f.size} values differ, rel err {rel_err(f, ref):.3e}"
+
+
+def test_tile_kernel_logic_with_every_boundary_kind(mirror):
+    """Regularized inlet, ExtrapolationOutflow outlet, Halfway body, 255 cells: the scalar boundary routine inside the tile path."""
+    from common import c_oracle_run
+
+    for name in ("warp_sphere_d3q19_bgk_fp32fp16", "warp_tunnel_d3q19_bgk_zouhe_pressure_fp32fp16"):
+        g0 = load_golden(name)
+        nx, ny, nz = g0["shape"]
+        # same boundary set on a tile-eligible grid (nz = 16): re-derive the index lists
+        shape = (nx, 32, 16)
+        lat = O.Lattice("D3Q19")
+        box, bne = O.bounding_box_indices(shape), O.bounding_box_indices(shape, remove_edges=True)
+        walls = np.unique(np.concatenate([box[k] for k in ("bottom", "top", "front", "back")], axis=1), axis=-1)
+        X, Y, Z = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+        body = np.array(np.where((X - shape[0] // 4) ** 2 + (Y - shape[1] // 2) ** 2 + (Z - shape[2] // 2) ** 2 < 9))
+        g = dict(g0)
+        g.update(shape=shape, steps=8, f_init=O.initialize_eq(shape, lat, "FP32FP16"))
+        bcs = []
+        for b in g0["bcs"]:
+            b = dict(b)
+            if b["kind"] == "fullway":
+                b["indices"] = walls
+            elif b["kind"] in ("regularized", "zouhe") and b["bc_type"] == "velocity":
+                b["indices"] = bne["left"]
+                pv = np.zeros((3, shape[1], shape[2]), np.float16)
+                pv[0] = 0.03
+                b["prescribed"] = pv
+            elif b["kind"] == "halfway":
+                b["indices"] = body
+            else:
+                b["indices"] = bne["right"]
+            bcs.append(b)
+        g["bcs"] = bcs
+        g["solid255"] = np.array([[shape[0] // 4], [shape[1] // 2], [shape[2] // 2]])  # one solid cell inside the body
+        ref, _, _ = c_oracle_run(g)
+        f = mirror_run(mirror, g, v=402)
+        assert np.array_equal(f, ref), f"{name}: {int((f != ref).sum())} of {f.size} values differ, rel err {rel_err(f, ref):.3e}"
+
+
+@pytest.mark.parametrize("name", ["cavity_d2q9_bgk_fp32", "cavity_d2q9_kbc_fp32", "channel2d_d2q9_bgk_outflow_fp32", "channel2d_d2q9_bgk_zouhe_pressure_fp32", "warp_channel2d_d2q9_bgk_regpressure"])
+def test_2d_slab_axis_order_gives_the_same_bits(mirror, name):
+    """D2Q9X (csrc/lattice.cuh): the axis order 2-D x-slab runs use — physical x on the kernel's ghost-plane axis, extents (nx, 1, ny) —
+    against the ordinary 2-D order (1, nx, ny): identical populations, BC normals and outflow neighbour reads included."""
+    g = load_golden(name)
+    assert np.array_equal(mirror_run(mirror, g, slab_axes=True), mirror_run(mirror, g))

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import LATE_CASES, RTOL, STEP_CASES, WARP_CASES, WARP_CASES_FP16, WARP_CASES_N4, c_oracle_run, load_golden, native_case, native_run, oracle_masks, rel_err, rel_err_elem, unpack_bits
+from common import LATE_CASES, RTOL, STEP_CASES, WARP_CASES, WARP_CASES_FP16, WARP_CASES_N4, c_oracle_run, load_golden, native_case, native_run, oracle_masks, rel_err, rel_err_elem, tile_case, unpack_bits
 from oracle import lbm_c
 
 pytestmark = pytest.mark.gpu
@@ -122,3 +122,52 @@ def test_omega_may_change_every_step_without_a_host_sync():
         g_0.copy_(state)
         g_0, g_1 = fresh(g_0, g_1, bm2, mm2, 1.45, 4)
         assert torch.equal(f_1, g_1), f"ramped stepper vs fresh stepper (cells_per_thread={v})"
+
+
+TILE_SHAPES = [("D3Q19", (3, 4, 512), True), ("D3Q19", (4, 8, 128), True), ("D3Q27", (3, 16, 64), True), ("D3Q19", (2, 64, 8), False), ("D3Q27", (5, 2, 256), False),
+               ("D3Q19", (1, 32, 16), True), ("D3Q19", (40, 64, 64), True), ("D3Q27", (33, 32, 128), True)]  # fmt: skip
+
+
+@pytest.mark.parametrize("lattice,shape,walls", TILE_SHAPES)
+def test_tile_kernel_is_bit_identical_to_the_reference_kernel(lattice, shape, walls):
+    """cells_per_thread 402: the persistent TMA-fed tile kernel (csrc/step_tile.cuh).  Closed boxes (lid + walls) and periodic boxes from a
+    seeded random state, FP32FP16, 12 steps: every population equal to the C restatement of the reference kernel, bit for bit, and to
+    the direct half2-state kernel."""
+    g = tile_case(lattice, shape, 12, 11, walls)
+    ref, _, _ = c_oracle_run(g)
+    f, _, _ = native_run(g, cells_per_thread=402)
+    assert np.array_equal(f, ref), f"{int((f != ref).sum())} of {f.size} values differ from the reference kernel's, rel err {rel_err(f, ref):.3e}"
+    f2, _, _ = native_run(g, cells_per_thread=202)
+    assert np.array_equal(f, f2)
+
+
+def test_tile_kernel_with_every_boundary_kind_and_solid_cells():
+    """Regularized inlet, ExtrapolationOutflow outlet, Halfway body, Fullway walls and cells with id 255 inside the tile path."""
+    from oracle import lbm_numpy as O
+
+    g0 = load_golden("warp_sphere_d3q19_bgk_fp32fp16")
+    shape = (48, 32, 64)
+    lat = O.Lattice("D3Q19")
+    box, bne = O.bounding_box_indices(shape), O.bounding_box_indices(shape, remove_edges=True)
+    walls = np.unique(np.concatenate([box[k] for k in ("bottom", "top", "front", "back")], axis=1), axis=-1)
+    X, Y, Z = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+    body = np.array(np.where((X - 12) ** 2 + (Y - 16) ** 2 + (Z - 32) ** 2 < 30))
+    pv = np.zeros((3, shape[1], shape[2]), np.float16)
+    pv[0] = 0.03
+    g = dict(g0)
+    g.update(shape=shape, steps=40, f_init=O.initialize_eq(shape, lat, "FP32FP16"))
+    g["bcs"] = [dict(kind="fullway", id=1, indices=walls), dict(kind="regularized", id=2, indices=bne["left"], bc_type="velocity", prescribed=pv),
+                dict(kind="outflow", id=3, indices=bne["right"]), dict(kind="halfway", id=4, indices=body)]  # fmt: skip
+    g["solid255"] = np.array([[12], [16], [32]])
+    ref, _, _ = c_oracle_run(g)
+    for v in (402, 202, 1):
+        f, _, _ = native_run(g, cells_per_thread=v)
+        assert np.array_equal(f, ref), f"cells_per_thread={v}: {int((f != ref).sum())} of {f.size} values differ, rel err {rel_err(f, ref):.3e}"
+
+
+def test_tile_kernel_refuses_shapes_it_cannot_tile():
+    g = load_golden("cavity_d3q19_bgk_fp32fp16")  # 16^3: a tile would be 32 rows, ny = 16
+    with pytest.raises(Exception, match="tile kernel needs"):
+        native_run(g, cells_per_thread=402)
+    with pytest.raises(Exception, match="FP32FP16 BGK"):
+        native_run(load_golden("cavity_d3q19_bgk_fp32"), cells_per_thread=402)

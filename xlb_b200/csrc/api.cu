@@ -57,6 +57,9 @@ template <> int dispatch_step<D2Q9, XLBN_BGK | kF>(const StepCall&);
 template <> int dispatch_step<D2Q9, XLBN_KBC | kF>(const StepCall&);
 template <> int dispatch_step<D3Q27, XLBN_KBC | kLeanKbc>(const StepCall&);  // tuning variant (cells_per_thread = 301)
 template <> int dispatch_step<D2Q9, XLBN_KBC | kLeanKbc>(const StepCall&);
+template <> int dispatch_step<D2Q9X, XLBN_BGK>(const StepCall&);  // 2-D x-slab axis order (step_inst_d2q9x.cu)
+template <> int dispatch_step<D2Q9X, XLBN_KBC>(const StepCall&);
+template <> int dispatch_step<D2Q9X, XLBN_KBC | kLeanKbc>(const StepCall&);
 }  // namespace xlbn
 
 extern "C" {
@@ -85,6 +88,7 @@ int xlbn_lattice_tables(int lattice, int32_t* c, double* w, int32_t* opp) {
 }
 
 int xlbn_stepper_create(const xlbn_stepper_desc* desc, xlbn_stepper** out) {
+  XLBN_RANGE("xlbn_stepper_create");
   if (!desc || !out) return fail(XLBN_E_ARG, "stepper_create: NULL argument");
   if (desc->lattice < XLBN_D2Q9 || desc->lattice > XLBN_D3Q27) return fail(XLBN_E_ARG, "stepper_create: unknown lattice %d", desc->lattice);
   if (desc->collision != XLBN_BGK && desc->collision != XLBN_KBC && desc->collision != XLBN_SMAGORINSKY_LES_BGK)
@@ -98,7 +102,7 @@ int xlbn_stepper_create(const xlbn_stepper_desc* desc, xlbn_stepper** out) {
   if (desc->compute_dtype == XLBN_F32 && desc->store_dtype == XLBN_F64) return fail(XLBN_E_DTYPE, "stepper_create: no FP32FP64 policy");
   if (desc->n_bc < 0 || (desc->n_bc > 0 && !desc->bcs)) return fail(XLBN_E_ARG, "stepper_create: bad BC list");
   const int cpt = desc->cells_per_thread;
-  if (cpt != 0 && cpt != 1 && cpt != 2 && cpt != 4 && cpt != 8 && cpt != 102 && cpt != 104 && cpt != 202 && cpt != 203 && cpt != 300 && cpt != 301)
+  if (cpt != 0 && cpt != 1 && cpt != 2 && cpt != 4 && cpt != 8 && cpt != 102 && cpt != 104 && cpt != 202 && cpt != 203 && cpt != 300 && cpt != 301 && cpt != 402 && cpt != 403)
     return fail(XLBN_E_ARG, "stepper_create: cells_per_thread = %d", cpt);
   if ((cpt == 300 || cpt == 301) && desc->collision != XLBN_KBC)
     return fail(XLBN_E_ARG, "stepper_create: cells_per_thread = %d selects a KBC formulation; the stepper's collision is %d", cpt, desc->collision);
@@ -146,6 +150,7 @@ int xlbn_stepper_create(const xlbn_stepper_desc* desc, xlbn_stepper** out) {
 }
 
 int xlbn_stepper_destroy(xlbn_stepper* s) {
+  XLBN_RANGE("xlbn_stepper_destroy");
   if (!s) return 0;
   if (s->table) cudaFree(s->table);
   delete s;
@@ -168,6 +173,7 @@ int xlbn_stepper_set_smagorinsky(xlbn_stepper* s, double coefficient) {
 }
 
 int xlbn_stepper_prepare(xlbn_stepper* s, double omega, void* stream) {
+  XLBN_RANGE("xlbn_stepper_prepare");
   if (!s) return fail(XLBN_E_ARG, "stepper_prepare: NULL stepper");
   // only the FP32FP16 BGK pair path reads per-omega constants (BcEntry::eq_out of EquilibriumBC entries)
   if (!s->has_equilibrium_bc || s->compute_dtype != XLBN_F32 || s->store_dtype != XLBN_F16 || s->collision != XLBN_BGK || s->forced) return 0;
@@ -186,6 +192,7 @@ int xlbn_stepper_prepare(xlbn_stepper* s, double omega, void* stream) {
 
 int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask, const uint32_t* missing_bits, const xlbn_domain* dom, double omega,
               int timestep, xlbn_halo* halo, void* stream) {
+  XLBN_RANGE("xlbn_step");
   if (!s || !f0 || !f1 || !bc_mask || !dom) return fail(XLBN_E_ARG, "xlbn_step: NULL argument");
   if (f0 == f1) return fail(XLBN_E_ARG, "xlbn_step: f0 and f1 must be different buffers (pull scheme)");
   if (s->needs_missing && !missing_bits) return fail(XLBN_E_ARG, "xlbn_step: this stepper has BCs that read the missing-direction bitmask");
@@ -216,9 +223,15 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
   c.out_lo = c.out_hi = nullptr;
   for (int a = 0; a < 3; ++a) c.force[a] = s->force[a];  // physical components; the cell algebra uses L::c(), not kernel axes
   c.smagorinsky = s->smagorinsky;
-  if (s->lattice == XLBN_D2Q9) {  // run [q][nx][ny] as kernel extents (1, nx, ny): unit-stride axis = thread axis
-    if (halo) return fail(XLBN_E_UNSUPPORTED, "xlbn_step: x-slab halo is not available for 2-D lattices");
-    if (dom->x_begin != 0 || dom->x_count != dom->nx) return fail(XLBN_E_UNSUPPORTED, "xlbn_step: partial x range is not available for 2-D lattices");
+  const bool slab_2d = s->lattice == XLBN_D2Q9 && (halo || dom->x_begin != 0 || dom->x_count != dom->nx);
+  if (slab_2d) {  // x-slab / partial x range in 2-D: kernel extents (nx, 1, ny), physical x on the kernel's slab axis (D2Q9X)
+    if (s->forced) return fail(XLBN_E_UNSUPPORTED, "xlbn_step: forced collision on a 2-D slab / partial x range is not built");
+    c.nx = dom->nx;
+    c.ny = 1;
+    c.nz = dom->ny;
+    c.x_begin = dom->x_begin;
+    c.x_count = dom->x_count;
+  } else if (s->lattice == XLBN_D2Q9) {  // run [q][nx][ny] as kernel extents (1, nx, ny): unit-stride axis = thread axis
     c.nx = 1;
     c.ny = dom->nx;
     c.nz = dom->ny;
@@ -267,6 +280,14 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
       }
       break;
     case XLBN_D2Q9:
+      if (slab_2d) {
+        switch (coll) {
+          case XLBN_BGK: return dispatch_step<D2Q9X, XLBN_BGK>(c);
+          case XLBN_KBC: return dispatch_step<D2Q9X, XLBN_KBC>(c);
+          case XLBN_KBC | kLeanKbc: return dispatch_step<D2Q9X, XLBN_KBC | kLeanKbc>(c);
+        }
+        break;
+      }
       switch (coll) {
         case XLBN_BGK: return dispatch_step<D2Q9, XLBN_BGK>(c);
         case XLBN_KBC: return dispatch_step<D2Q9, XLBN_KBC>(c);

@@ -24,6 +24,7 @@ static int lattice_ndir(int lattice) {
   switch (lattice) {
     case XLBN_D3Q19: return D3Q19::n_xdir();
     case XLBN_D3Q27: return D3Q27::n_xdir();
+    case XLBN_D2Q9: return D2Q9X::n_xdir();  // 2-D slabs run in the D2Q9X axis order (lattice.cuh)
     default: return -1;
   }
 }
@@ -89,9 +90,10 @@ using namespace xlbn;
 extern "C" {
 
 int xlbn_halo_create(int lattice, int store_dtype, int ny, int nz, xlbn_halo** out) {
+  XLBN_RANGE("xlbn_halo_create");
   if (!out) return fail(XLBN_E_ARG, "halo_create: out is NULL");
   const int ndir = lattice_ndir(lattice);
-  if (ndir < 0) return fail(XLBN_E_UNSUPPORTED, "halo: x-slab decomposition is implemented for D3Q19 / D3Q27 (lattice %d)", lattice);
+  if (ndir < 0) return fail(XLBN_E_UNSUPPORTED, "halo: unknown lattice %d", lattice);
   if (!is_float_dtype(store_dtype)) return fail(XLBN_E_DTYPE, "halo: bad store dtype %d", store_dtype);
   if (ny <= 0 || nz <= 0) return fail(XLBN_E_SHAPE, "halo: ny=%d nz=%d", ny, nz);
   xlbn_halo* h = new xlbn_halo();
@@ -136,6 +138,7 @@ int xlbn_halo_create(int lattice, int store_dtype, int ny, int nz, xlbn_halo** o
 }
 
 int xlbn_halo_destroy(xlbn_halo* h) {
+  XLBN_RANGE("xlbn_halo_destroy");
   if (!h) return 0;
   if (h->ipc_lo && h->peer_lo) cudaIpcCloseMemHandle(h->peer_lo);
   if (h->ipc_hi && h->peer_hi && h->peer_hi != h->peer_lo) cudaIpcCloseMemHandle(h->peer_hi);
@@ -158,6 +161,7 @@ int xlbn_halo_timed_out(xlbn_halo* h) {
 }
 
 int xlbn_halo_export(xlbn_halo* h, unsigned char handle[64]) {
+  XLBN_RANGE("xlbn_halo_export");
   if (!h || !handle) return fail(XLBN_E_ARG, "halo_export: NULL");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   cudaIpcMemHandle_t ipc;
@@ -167,6 +171,7 @@ int xlbn_halo_export(xlbn_halo* h, unsigned char handle[64]) {
 }
 
 int xlbn_halo_connect(xlbn_halo* h, const unsigned char lo_handle[64], const unsigned char hi_handle[64], int same_process) {
+  XLBN_RANGE("xlbn_halo_connect");
   if (!h || !lo_handle || !hi_handle) return fail(XLBN_E_ARG, "halo_connect: NULL");
   if (same_process) {
     memcpy(&h->peer_lo, lo_handle, sizeof(char*));
@@ -191,6 +196,7 @@ int xlbn_halo_connect(xlbn_halo* h, const unsigned char lo_handle[64], const uns
 }
 
 int xlbn_halo_push(xlbn_halo* h, const void* f, const xlbn_domain* dom, int timestep, void* stream) {
+  XLBN_RANGE("xlbn_halo_push");
   if (!h || !f || !dom) return fail(XLBN_E_ARG, "halo_push: NULL");
   if (!h->connected) return fail(XLBN_E_STATE, "halo_push: halo is not connected");
   if (int e = halo_check_alive(h, "halo_push")) return e;
@@ -207,6 +213,9 @@ int xlbn_halo_push(xlbn_halo* h, const void* f, const xlbn_domain* dom, int time
   if (h->lattice == XLBN_D3Q19) {
     halo_push_kernel<D3Q19><<<blocks, 256, 0, st>>>(fc, to_hi, +1, dom->nx - 1, plane, n, esize);
     halo_push_kernel<D3Q19><<<blocks, 256, 0, st>>>(fc, to_lo, -1, 0, plane, n, esize);
+  } else if (h->lattice == XLBN_D2Q9) {
+    halo_push_kernel<D2Q9X><<<blocks, 256, 0, st>>>(fc, to_hi, +1, dom->nx - 1, plane, n, esize);
+    halo_push_kernel<D2Q9X><<<blocks, 256, 0, st>>>(fc, to_lo, -1, 0, plane, n, esize);
   } else {
     halo_push_kernel<D3Q27><<<blocks, 256, 0, st>>>(fc, to_hi, +1, dom->nx - 1, plane, n, esize);
     halo_push_kernel<D3Q27><<<blocks, 256, 0, st>>>(fc, to_lo, -1, 0, plane, n, esize);
@@ -216,6 +225,7 @@ int xlbn_halo_push(xlbn_halo* h, const void* f, const xlbn_domain* dom, int time
 }
 
 int xlbn_halo_signal(xlbn_halo* h, int timestep, void* stream) {
+  XLBN_RANGE("xlbn_halo_signal");
   if (!h) return fail(XLBN_E_ARG, "halo_signal: NULL");
   if (!h->connected) return fail(XLBN_E_STATE, "halo_signal: halo is not connected");
   if (int e = halo_check_alive(h, "halo_signal")) return e;
@@ -226,6 +236,7 @@ int xlbn_halo_signal(xlbn_halo* h, int timestep, void* stream) {
 }
 
 int xlbn_halo_wait(xlbn_halo* h, int timestep, void* stream) {
+  XLBN_RANGE("xlbn_halo_wait");
   if (!h) return fail(XLBN_E_ARG, "halo_wait: NULL");
   if (!h->connected) return fail(XLBN_E_STATE, "halo_wait: halo is not connected");
   if (int e = halo_check_alive(h, "halo_wait")) return e;

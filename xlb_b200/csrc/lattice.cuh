@@ -24,6 +24,7 @@ struct D3Q27Base {
   XLBN_HD static int digit(int i) { return i == 0 ? 0 : (i == 1 ? -1 : 1); }
   XLBN_HD static int ck(int axis, int l) { return axis == 0 ? digit(l / 9) : (axis == 1 ? digit((l / 3) % 3) : digit(l % 3)); }
   XLBN_HD static double w_by_speed(int s) { return s == 0 ? 8.0 / 27.0 : (s == 1 ? 2.0 / 27.0 : (s == 2 ? 1.0 / 54.0 : 1.0 / 216.0)); }
+  XLBN_HD static int kaxis(int a) { return a; }  // kernel axis of physical axis a
 };
 
 struct D3Q19Base {
@@ -34,6 +35,7 @@ struct D3Q19Base {
   }
   XLBN_HD static int ck(int axis, int l) { return D3Q27Base::ck(axis, idx27(l)); }
   XLBN_HD static double w_by_speed(int s) { return s == 0 ? 1.0 / 3.0 : (s == 1 ? 1.0 / 18.0 : 1.0 / 36.0); }
+  XLBN_HD static int kaxis(int a) { return a; }
 };
 
 struct D2Q9Base {
@@ -44,6 +46,16 @@ struct D2Q9Base {
     return axis == 0 ? 0 : (axis == 1 ? cx[l] : cy[l]);
   }
   XLBN_HD static double w_by_speed(int s) { return s == 0 ? 4.0 / 9.0 : (s == 1 ? 1.0 / 9.0 : 1.0 / 36.0); }
+  XLBN_HD static int kaxis(int a) { return a + 1; }
+};
+
+// D2Q9 for x-slab runs: the same velocity set with physical x on kernel axis 0 (the slab axis, ghost planes) and physical y on the
+// unit-stride thread axis; the kernel's middle axis has extent 1.  A [q][nx][ny] field is then run as kernel extents (nx, 1, ny).
+struct D2Q9XBase {
+  static constexpr int D = 2, Q = 9, ID = XLBN_D2Q9;
+  XLBN_HD static int ck(int axis, int l) { return axis == 0 ? D2Q9Base::ck(1, l) : (axis == 1 ? 0 : D2Q9Base::ck(2, l)); }
+  XLBN_HD static double w_by_speed(int s) { return D2Q9Base::w_by_speed(s); }
+  XLBN_HD static int kaxis(int a) { return a == 0 ? 0 : 2; }
 };
 
 template <class B>
@@ -53,7 +65,8 @@ struct Lattice : B {
   static constexpr int NT = D * (D + 1) / 2;  // independent components of a symmetric DxD tensor
 
   XLBN_HD static int iabs(int v) { return v < 0 ? -v : v; }
-  XLBN_HD static int c(int a, int l) { return B::ck(a + 3 - D, l); }  // physical component a of velocity l
+  XLBN_HD static int kaxis(int a) { return B::kaxis(a); }
+  XLBN_HD static int c(int a, int l) { return B::ck(B::kaxis(a), l); }  // physical component a of velocity l
   XLBN_HD static int speed(int l) { return iabs(B::ck(0, l)) + iabs(B::ck(1, l)) + iabs(B::ck(2, l)); }
   XLBN_HD static double w(int l) { return B::w_by_speed(speed(l)); }
   XLBN_HD static int opp(int l) {
@@ -98,6 +111,7 @@ struct Lattice : B {
 using D3Q19 = Lattice<D3Q19Base>;
 using D3Q27 = Lattice<D3Q27Base>;
 using D2Q9 = Lattice<D2Q9Base>;
+using D2Q9X = Lattice<D2Q9XBase>;
 
 // Call fn(integral_constant<int, I>) for I = 0..N-1: a loop whose index is a constant expression in the body, so the
 // lattice tables above are evaluated at compile time.

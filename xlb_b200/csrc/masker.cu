@@ -78,7 +78,7 @@ __global__ void mask_indices_kernel(int mode, const int32_t* idx, long long n_id
 }
 
 template <class L>
-__global__ void mask_finalize_jax_kernel(MaskGeom m, uint8_t* missing, const uint8_t* solid) {
+__global__ void mask_finalize_jax_kernel(MaskGeom m, uint8_t* missing, const uint8_t* solid, const uint8_t* incoming) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m.cells) return;
   const int z = (int)(i % m.n[2]) + m.s[2];
@@ -90,6 +90,13 @@ __global__ void mask_finalize_jax_kernel(MaskGeom m, uint8_t* missing, const uin
     if (!miss) {
       const long long sh = solid_index(m, sx, sy, sz);
       miss = sh >= 0 && solid[sh] != 0;
+      // entries the caller's mask already held travel with the stream as well (the reference pads the INCOMING mask and streams it,
+      // indices_boundary_masker.py:56-63, 92): only sources inside this slab can be seen here
+      if (!miss && incoming) {
+        const int lx = sx - m.s[0], ly = sy - m.s[1], lz = sz - m.s[2];
+        if (lx >= 0 && lx < m.n[0] && ly >= 0 && ly < m.n[1] && lz >= 0 && lz < m.n[2])
+          miss = incoming[(long long)l * m.cells + ((long long)lx * m.n[1] + ly) * m.n[2] + lz] != 0;
+      }
     }
     missing[(long long)l * m.cells + i] = miss ? 1 : 0;
   XLBN_END
@@ -124,6 +131,7 @@ extern "C" {
 
 int xlbn_mask_indices(int lattice, int mode, const int32_t* indices, long long n, int bc_id, int needs_padding, const int32_t global_dims[3],
                       const int32_t start[3], const int32_t local_dims[3], uint8_t* bc_mask, uint8_t* missing, uint8_t* solid, void* stream) {
+  XLBN_RANGE("xlbn_mask_indices");
   MaskGeom m;
   if (int e = make_geom(global_dims, start, local_dims, &m)) return e;
   if (n < 0) return fail(XLBN_E_ARG, "mask: negative index count");
@@ -145,16 +153,18 @@ int xlbn_mask_indices(int lattice, int mode, const int32_t* indices, long long n
 }
 
 int xlbn_mask_finalize_jax(int lattice, const int32_t global_dims[3], const int32_t start[3], const int32_t local_dims[3], uint8_t* missing,
-                           const uint8_t* solid, void* stream) {
+                           const uint8_t* solid, const uint8_t* incoming, void* stream) {
+  XLBN_RANGE("xlbn_mask_finalize_jax");
   MaskGeom m;
   if (int e = make_geom(global_dims, start, local_dims, &m)) return e;
   if (!missing || !solid) return fail(XLBN_E_ARG, "mask finalize: NULL array");
+  if (incoming == missing) return fail(XLBN_E_ARG, "mask finalize: `incoming` must be a copy of the caller's mask, not the output array");
   const unsigned blocks = (unsigned)((m.cells + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   switch (lattice) {
-    case XLBN_D2Q9: mask_finalize_jax_kernel<D2Q9><<<blocks, 256, 0, st>>>(m, missing, solid); break;
-    case XLBN_D3Q19: mask_finalize_jax_kernel<D3Q19><<<blocks, 256, 0, st>>>(m, missing, solid); break;
-    case XLBN_D3Q27: mask_finalize_jax_kernel<D3Q27><<<blocks, 256, 0, st>>>(m, missing, solid); break;
+    case XLBN_D2Q9: mask_finalize_jax_kernel<D2Q9><<<blocks, 256, 0, st>>>(m, missing, solid, incoming); break;
+    case XLBN_D3Q19: mask_finalize_jax_kernel<D3Q19><<<blocks, 256, 0, st>>>(m, missing, solid, incoming); break;
+    case XLBN_D3Q27: mask_finalize_jax_kernel<D3Q27><<<blocks, 256, 0, st>>>(m, missing, solid, incoming); break;
     default: return fail(XLBN_E_ARG, "unknown lattice %d", lattice);
   }
   XLBN_LAUNCH_OK("mask_finalize_jax_kernel");
@@ -162,6 +172,7 @@ int xlbn_mask_finalize_jax(int lattice, const int32_t global_dims[3], const int3
 }
 
 int xlbn_pack_missing(int q, const uint8_t* missing, uint32_t* bits, long long n_cells, void* stream) {
+  XLBN_RANGE("xlbn_pack_missing");
   if (q <= 0 || q > 32) return fail(XLBN_E_ARG, "pack_missing: q = %d", q);
   if (!missing || !bits || n_cells < 0) return fail(XLBN_E_ARG, "pack_missing: bad argument");
   if (n_cells == 0) return 0;

@@ -294,6 +294,7 @@ using namespace xlbn;
 extern "C" {
 
 int xlbn_stream(int lattice, const void* f_in, void* f_out, int dtype, const int32_t dims[3], void* stream) {
+  XLBN_RANGE("xlbn_stream");
   if (int e = check_dims(lattice, dims)) return e;
   if (!f_in || !f_out) return fail(XLBN_E_ARG, "xlbn_stream: NULL array");
   if (f_in == f_out) return fail(XLBN_E_ARG, "xlbn_stream: in-place streaming is not supported");
@@ -306,6 +307,7 @@ int xlbn_stream(int lattice, const void* f_in, void* f_out, int dtype, const int
 
 int xlbn_equilibrium(int lattice, int compute_dtype, const void* rho, int rho_dtype, const void* u, int u_dtype, void* f, int f_dtype,
                      const int32_t dims[3], void* stream) {
+  XLBN_RANGE("xlbn_equilibrium");
   if (int e = check_dims(lattice, dims)) return e;
   if (!rho || !u || !f) return fail(XLBN_E_ARG, "xlbn_equilibrium: NULL array");
   XLBN_REQUIRE_FLOAT(rho_dtype, "rho");
@@ -320,6 +322,7 @@ int xlbn_equilibrium(int lattice, int compute_dtype, const void* rho, int rho_dt
 
 int xlbn_macroscopic(int lattice, int compute_dtype, const void* f, int f_dtype, void* rho, int rho_dtype, void* u, int u_dtype,
                      const int32_t dims[3], void* stream) {
+  XLBN_RANGE("xlbn_macroscopic");
   if (int e = check_dims(lattice, dims)) return e;
   if (!f || (!rho && !u)) return fail(XLBN_E_ARG, "xlbn_macroscopic: NULL array");
   XLBN_REQUIRE_FLOAT(f_dtype, "f");
@@ -334,6 +337,7 @@ int xlbn_macroscopic(int lattice, int compute_dtype, const void* f, int f_dtype,
 
 int xlbn_first_moment(int lattice, int compute_dtype, const void* f, int f_dtype, const void* rho, int rho_dtype, void* u, int u_dtype,
                       const int32_t dims[3], void* stream) {
+  XLBN_RANGE("xlbn_first_moment");
   if (int e = check_dims(lattice, dims)) return e;
   if (!f || !rho || !u) return fail(XLBN_E_ARG, "xlbn_first_moment: NULL array");
   XLBN_REQUIRE_FLOAT(f_dtype, "f");
@@ -348,6 +352,7 @@ int xlbn_first_moment(int lattice, int compute_dtype, const void* f, int f_dtype
 
 int xlbn_second_moment(int lattice, int compute_dtype, const void* f, int f_dtype, void* pi, int pi_dtype, const int32_t dims[3],
                        void* stream) {
+  XLBN_RANGE("xlbn_second_moment");
   if (int e = check_dims(lattice, dims)) return e;
   if (!f || !pi) return fail(XLBN_E_ARG, "xlbn_second_moment: NULL array");
   XLBN_REQUIRE_FLOAT(f_dtype, "f");
@@ -361,6 +366,7 @@ int xlbn_second_moment(int lattice, int compute_dtype, const void* f, int f_dtyp
 
 int xlbn_collide(int lattice, int collision, int compute_dtype, const void* f, int f_dtype, const void* feq, int feq_dtype, void* fout,
                  int fout_dtype, const void* rho, int rho_dtype, double omega, const int32_t dims[3], void* stream) {
+  XLBN_RANGE("xlbn_collide");
   if (int e = check_dims(lattice, dims)) return e;
   if (!f || !feq || !fout) return fail(XLBN_E_ARG, "xlbn_collide: NULL array");
   XLBN_REQUIRE_FLOAT(f_dtype, "f");
@@ -394,6 +400,7 @@ int xlbn_collide(int lattice, int collision, int compute_dtype, const void* f, i
 int xlbn_collide_ext(int lattice, int collision, int compute_dtype, const void* f, int f_dtype, const void* feq, int feq_dtype, void* fout,
                      int fout_dtype, const void* rho, int rho_dtype, const void* u, int u_dtype, double omega, const double* force,
                      double smagorinsky, const int32_t dims[3], void* stream) {
+  XLBN_RANGE("xlbn_collide_ext");
   if (int e = check_dims(lattice, dims)) return e;
   if (!f || !feq || !fout) return fail(XLBN_E_ARG, "xlbn_collide_ext: NULL array");
   XLBN_REQUIRE_FLOAT(f_dtype, "f");
@@ -446,6 +453,7 @@ int xlbn_collide_ext(int lattice, int collision, int compute_dtype, const void* 
 int xlbn_exact_difference(int lattice, int compute_dtype, const void* f_postcollision, int f_dtype, const void* feq, int feq_dtype, void* fout,
                           int fout_dtype, const void* rho, int rho_dtype, const void* u, int u_dtype, const double* force, const int32_t dims[3],
                           void* stream) {
+  XLBN_RANGE("xlbn_exact_difference");
   if (int e = check_dims(lattice, dims)) return e;
   if (!f_postcollision || !feq || !fout || !rho || !u || !force) return fail(XLBN_E_ARG, "xlbn_exact_difference: NULL argument");
   XLBN_REQUIRE_FLOAT(f_dtype, "f_postcollision");
@@ -464,6 +472,7 @@ int xlbn_exact_difference(int lattice, int compute_dtype, const void* f_postcoll
 
 int xlbn_bc_apply(int lattice, int compute_dtype, const xlbn_bc_desc* bc, const void* f_pre, void* f_post, int dtype, const uint8_t* bc_mask,
                   const uint8_t* missing, const int32_t dims[3], void* stream) {
+  XLBN_RANGE("xlbn_bc_apply");
   if (int e = check_dims(lattice, dims)) return e;
   if (!bc || !f_pre || !f_post || !bc_mask || !missing) return fail(XLBN_E_ARG, "xlbn_bc_apply: NULL argument");
   XLBN_REQUIRE_FLOAT(dtype, "f_pre/f_post");
@@ -479,6 +488,7 @@ int xlbn_bc_apply(int lattice, int compute_dtype, const xlbn_bc_desc* bc, const 
 
 int xlbn_momentum_transfer(int lattice, int compute_dtype, const xlbn_bc_desc* bc, const void* f0, const void* f1, int dtype,
                            const uint8_t* bc_mask, const uint8_t* missing, const int32_t dims[3], double* force, void* stream) {
+  XLBN_RANGE("xlbn_momentum_transfer");
   if (int e = check_dims(lattice, dims)) return e;
   if (!bc || !f0 || !bc_mask || !missing || !force) return fail(XLBN_E_ARG, "xlbn_momentum_transfer: NULL argument");
   XLBN_REQUIRE_FLOAT(dtype, "f_0");

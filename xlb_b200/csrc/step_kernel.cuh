@@ -274,7 +274,7 @@ XLBN_DEVFN __noinline__ void bc_cell(const StepParams<TS>& p, int id, int x, int
     int ni[L::D];
     bc_normal<L>(miss, ni);
     int nk[3] = {0, 0, 0};
-    XLBN_FOR(L::D, d) nk[d + 3 - L::D] = ni[d]; XLBN_END
+    XLBN_FOR(L::D, d) nk[L::kaxis(d)] = ni[d]; XLBN_END
     const TC cs = TC(0.57735026918962576451);
     TC aux[Q];
     XLBN_FOR(Q, l)
@@ -357,9 +357,10 @@ XLBN_DEV void store_cells(const StepParams<TS>& p, unsigned cell, const Pack<uin
   }
 }
 
-template <class L, int COLL, class TC, class TS, int V, int XC>
-XLBN_DEV void bc_tail(const StepParams<TS>& p, const Pack<uint8_t, V>& ids, const int x, const int y, const int z0, const unsigned cell,
-                      const bool any_solid, TC (&f)[V][L::Q]) {
+// Boundary handling of a thread's V cells IN REGISTERS: f holds the pulled populations on entry and the values to store on exit
+// (cells with id 255 are left as they are: the caller must not store them).
+template <class L, int COLL, class TC, class TS, int V>
+XLBN_DEV void bc_compute(const StepParams<TS>& p, const Pack<uint8_t, V>& ids, const int x, const int y, const int z0, TC (&f)[V][L::Q]) {
   constexpr int Q = L::Q;
   const TC omega = (TC)p.omega;
   // Threads with boundary cells.  The two kinds that make up closed-box walls and lids are handled in registers:
@@ -391,6 +392,12 @@ XLBN_DEV void bc_tail(const StepParams<TS>& p, const Pack<uint8_t, V>& ids, cons
       XLBN_FOR(Q, l) f[v][l] = tmp[l]; XLBN_END
     }
   }
+}
+
+template <class L, int COLL, class TC, class TS, int V, int XC>
+XLBN_DEV void bc_tail(const StepParams<TS>& p, const Pack<uint8_t, V>& ids, const int x, const int y, const int z0, const unsigned cell,
+                      const bool any_solid, TC (&f)[V][L::Q]) {
+  bc_compute<L, COLL, TC, TS, V>(p, ids, x, y, z0, f);
   if (any_solid) store_cells<L, TC, TS, V, XC, true>(p, cell, ids, f);
   else store_cells<L, TC, TS, V, XC, false>(p, cell, ids, f);
 }
@@ -572,6 +579,46 @@ __global__ void bc_precompute_kernel(BcEntry* table, float omega) {
   XLBN_FOR(L::Q, l) table[id].eq_out[l] = f[l]; XLBN_END
 }
 
+// The arithmetic of the half2-state paths: moments -> equilibrium -> BGK for the two cells held in h (packed fp32x2: both cells at once),
+// emit(l, out) receives the relaxed pair of population l.  One IEEE rounding per operation, in the reference's order (csrc/lbm_math.cuh
+// "ROUNDINGS"): bit-identical to the scalar path and to the reference kernel.
+template <class L, class Emit>
+XLBN_DEV void h2_collide_each(const __half2 (&h)[L::Q], const float omega_f, Emit&& emit) {
+  constexpr int Q = L::Q;
+  // moments (macroscopic.py:43-47)
+  f32x2 rho(0.0f), u[L::D];
+  XLBN_FOR(L::D, d) u[d] = f32x2(0.0f); XLBN_END
+  XLBN_FOR(Q, l)
+    const f32x2 f(__half22float2(h[l]));
+    rho += f;
+    XLBN_FOR(L::D, d)
+      if constexpr (L::c(d, l) == 1) u[d] += f;
+      else if constexpr (L::c(d, l) == -1) u[d] -= f;
+    XLBN_END
+  XLBN_END
+  // u = (sum c f) / rho, correctly rounded (first_moment.py:38)
+  const f32x2 inv = rcp_refined_(rho);
+  XLBN_FOR(L::D, d) u[d] = div_by_(u[d], rho, inv); XLBN_END
+  // mul_then_add_: a product that is rounded BEFORE the addition it feeds (see common.cuh: the compiler would contract the pair)
+  f32x2 uu = mul_then_add_(u[0], u[0]);
+  XLBN_FOR(L::D - 1, d) uu = uu + mul_then_add_(u[d + 1], u[d + 1]); XLBN_END
+  const f32x2 usqr = mul_then_add_(f32x2(1.5f), uu);
+  const f32x2 omega(omega_f);
+  // equilibrium + BGK relaxation per population (quadratic_equilibrium.py:35-60, bgk.py:30-34)
+  XLBN_FOR(Q, l)
+    const f32x2 f(__half22float2(h[l]));
+    f32x2 cu(0.0f);
+    XLBN_FOR(L::D, d)
+      if constexpr (L::c(d, l) == 1) cu += u[d];
+      else if constexpr (L::c(d, l) == -1) cu -= u[d];
+    XLBN_END
+    cu *= f32x2(3.0f);
+    // 1 + 0.5 cu may contract: the product is exact
+    const f32x2 feq = mul_then_add_(rho * f32x2(L::w(l)), f32x2(1.0f) + mul_then_add_(cu, f32x2(1.0f) + f32x2(0.5f) * cu) - usqr);
+    emit(l_, f - mul_then_add_(omega, f - feq));
+  XLBN_END
+}
+
 // moments + equilibrium + BGK + narrow + store for the two cells of a half2-state thread.  BCV = 2: per-half handling of
 // FullwayBounceBack (bit copy of the opposite population's half; fp16 -> fp32 -> fp16 is exact) and EquilibriumBC cells
 // (the precomputed constant update, BcEntry::eq_out); BCV = 1: FullwayBounceBack only (no table pointers, no constant
@@ -579,7 +626,6 @@ __global__ void bc_precompute_kernel(BcEntry* table, float omega) {
 template <class L, int XC, int BCV>
 XLBN_DEV void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L::Q], const unsigned cell, const int id_lo, const int id_hi) {
   using TS = __half;
-  constexpr int Q = L::Q;
   bool eq_lo = false, eq_hi = false, fw_lo = false, fw_hi = false;
   const float* out_lo = nullptr;
   const float* out_hi = nullptr;
@@ -595,35 +641,8 @@ XLBN_DEV void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L
     fw_lo = id_lo && p.kinds[id_lo] == XLBN_BC_FULLWAY_BOUNCE_BACK;
     fw_hi = id_hi && p.kinds[id_hi] == XLBN_BC_FULLWAY_BOUNCE_BACK;
   }
-  // moments (macroscopic.py:43-47)
-  f32x2 rho(0.0f), u[L::D];
-  XLBN_FOR(L::D, d) u[d] = f32x2(0.0f); XLBN_END
-  XLBN_FOR(Q, l)
-    const f32x2 f(__half22float2(h[l]));
-    rho += f;
-    XLBN_FOR(L::D, d)
-      if constexpr (L::c(d, l) == 1) u[d] += f;
-      else if constexpr (L::c(d, l) == -1) u[d] -= f;
-    XLBN_END
-  XLBN_END
-  // u = (sum c f) / rho, correctly rounded (first_moment.py:38); every operation below is one IEEE rounding in the reference's order
-  const f32x2 inv = rcp_refined_(rho);
-  XLBN_FOR(L::D, d) u[d] = div_by_(u[d], rho, inv); XLBN_END
-  f32x2 uu = u[0] * u[0];
-  XLBN_FOR(L::D - 1, d) uu = uu + u[d + 1] * u[d + 1]; XLBN_END
-  const f32x2 usqr = f32x2(1.5f) * uu;
-  const f32x2 omega((float)p.omega);
-  // equilibrium + BGK relaxation per population (quadratic_equilibrium.py:35-60, bgk.py:30-34), narrowed and stored at once
-  XLBN_FOR(Q, l)
-    const f32x2 f(__half22float2(h[l]));
-    f32x2 cu(0.0f);
-    XLBN_FOR(L::D, d)
-      if constexpr (L::c(d, l) == 1) cu += u[d];
-      else if constexpr (L::c(d, l) == -1) cu -= u[d];
-    XLBN_END
-    cu *= f32x2(3.0f);
-    const f32x2 feq = rho * f32x2(L::w(l)) * (f32x2(1.0f) + cu * (f32x2(1.0f) + f32x2(0.5f) * cu) - usqr);
-    f32x2 out = f - omega * (f - feq);
+  h2_collide_each<L>(h, (float)p.omega, [&](auto l_, f32x2 out) {
+    constexpr int l = decltype(l_)::value;
     if constexpr (BCV == 2) {  // bc_equilibrium.py:76-86 followed by the ordinary collision = a per-BC constant
       if (eq_lo) out.v.x = out_lo[l];
       if (eq_hi) out.v.y = out_hi[l];
@@ -642,7 +661,7 @@ XLBN_DEV void h2_collide_store(const StepParams<__half>& p, const __half2 (&h)[L
     } else if constexpr (L::ck(0, l) == -1 && (XC & 1)) {
       if (p.peer_lo[l]) gstore<TS, 2>(p.peer_lo[l] + cell, a);
     }
-  XLBN_END
+  });
 }
 
 // ---- half2-state pair path (FP32FP16, BGK): two cells per thread, populations kept as the loaded half2 words ---------------
@@ -771,6 +790,10 @@ __global__ void __launch_bounds__(StepTraits<L, COLL, TC, TS, V, MODE>::kThreads
   }
 }
 
+}  // namespace xlbn
+#include "step_tile.cuh"  // the persistent TMA-fed tile kernel (FP32FP16 BGK), built on the code above
+namespace xlbn {
+
 // ---- host-side launch ------------------------------------------------------------------------------------------------
 template <class L, int COLL, class TC, class TS, int V, int MODE = 0>
 int launch_step_v(const StepParams<TS>& p, int x_count, cudaStream_t stream) {
@@ -814,6 +837,25 @@ int launch_step_base(const StepParams<TS>& p, int x_count, int requested_v, cons
   int req = requested_v;
   constexpr bool can_h2 = sizeof(TC) == 4 && sizeof(TS) == 2 && COLL == XLBN_BGK;
   if (req == 0) req = can_h2 ? 202 : 1;
+#if !XLBN_ON_HOST
+  if (req == 402 || req == 403) {  // the tile kernel (step_tile.cuh), explicitly: 402 = two CTAs per SM, 403 = three (D3Q19)
+    if constexpr (can_h2 && L::D == 3) {
+      if (!tile_eligible<L>(p, f0, f1, g0, g1, o0 != nullptr || o1 != nullptr))
+        return fail(XLBN_E_SHAPE, "cells_per_thread = 402 / 403: the tile kernel needs nz | 512, nz %% 8 == 0, ny %% (512 / nz) == 0, 16-byte aligned arrays and no halo handle (nz = %d, ny = %d)", p.nz, p.ny);
+      if (eq_omega_state && !(p.omega == *eq_omega_state)) {
+        bc_precompute_kernel<L, COLL><<<1, 256, 0, stream>>>(table_rw, (float)p.omega);
+        XLBN_LAUNCH_OK("bc_precompute_kernel");
+        *eq_omega_state = p.omega;
+      }
+      if constexpr (L::Q <= 19) {
+        if (req == 403) return launch_step_tile<L, 3>(p, x_count, stream);
+      }
+      return launch_step_tile<L, 2>(p, x_count, stream);
+    } else {
+      return fail(XLBN_E_ARG, "cells_per_thread = 402 / 403: the tile kernel exists for FP32FP16 BGK on 3-D lattices only");
+    }
+  }
+#endif
   if (req == 202 || req == 203) {
     if constexpr (can_h2) {
       if (pick_cells_per_thread(2, 1, (int)sizeof(TS), p.nz, p.bc, {f0, f1, g0, g1, o0, o1}) == 2) {

@@ -1,0 +1,329 @@
+// The tile kernel: the fused step as a PERSISTENT, TMA-FED pipeline (FP32FP16 storage, BGK).  Same per-cell algebra, same results —
+// bit for bit — as step_kernel's half2-state path; what changes is how the bytes move.
+//
+// Why.  With fp16 storage the step moves 77 B per cell and needs ~230 instructions per cell: the direct-load kernel keeps at most
+// 32 warps/SM resident (64 registers, two cells per thread), every one of them parked on its own 29 loads (ncu: long_scoreboard 62 %,
+// one eligible warp per cycle, 26 of 64 warp slots) — it stops at 0.71 (cavity) / 0.84 (periodic) of the HBM roofline, and 40 % of
+// its integer work is 64-bit address arithmetic for 48 global accesses per thread.  Memory-level parallelism is tied to registers.
+//
+// Design (Blackwell: bulk asynchronous copies = TMA in 1-D form, mbarrier transaction counts, 227 KB of shared memory per SM).
+//   * A TILE is 512 consecutive cells of one x-plane: R = 512 / nz whole rows (nz | 512).  For population l the tile's post-stream
+//     values come from rows y - c_y of plane x - c_x: ONE contiguous run of 1 KB in global memory (two at the periodic y wrap), and
+//     the c_z = +-1 shift is a one-element rotation inside each row — applied when the row is read back from shared memory.
+//   * One PRODUCER warp per CTA: lane l issues population l's bulk copy (cp.async.bulk global -> shared, completion counted on the
+//     stage's mbarrier), one more lane the tile's 512 bc ids.  A handful of address computations per TILE instead of per thread.
+//     It runs ahead through a ring of input stages: the bytes in flight per SM are set by shared memory (2 CTAs x 3 stages x 19.5 KB
+//     for D3Q19), not by registers or occupancy.
+//   * 8 CONSUMER warps (256 threads x two z-neighbours): wait for the stage, read their half2 words with immediate-offset LDS (the
+//     rotated rows take a second word and one PRMT), release the stage at once — a warp's arrival on the stage's "empty" mbarrier —
+//     collide in packed fp32x2 and store the half2 results straight to global memory (coalesced 128 B per warp and population;
+//     stores never stall a warp).  Consumer warps never meet at a CTA barrier: the first version staged the results in shared memory
+//     for bulk stores and spent 28 % of its stall samples at that barrier (profiles/r2_ncu_tile_v1_*).
+//   * Boundary cells.  FullwayBounceBack halves are a masked select of the opposite population's word, chosen per warp only when the
+//     warp holds a boundary cell; EquilibriumBC halves are overwritten with the per-BC constant update (2-byte stores after the pair
+//     store); any other kind, and cells with id 255 (never written), go through the scalar boundary routine of the direct kernel.
+// Eligibility (xlbn_step falls back to the direct kernel otherwise): FP32FP16, BGK, no halo handle on the call (face planes of a slab
+// store into peer memory: direct kernel), nz a divisor of 512 and a multiple of 8, ny a multiple of 512 / nz, 16-byte aligned arrays.
+// Included by step_kernel.cuh (after the per-cell code it builds on, before the host-side launch code); not a stand-alone header.
+#pragma once
+
+namespace xlbn {
+
+constexpr int kTileCells = 512;
+constexpr int kTileConsumers = 256;               // consumer threads = half2 words per population row of a tile
+constexpr int kTileThreads = kTileConsumers + 32;  // + the producer warp
+constexpr int kTileRowBytes = kTileCells * 2;
+constexpr int kTileBarBytes = 128;
+
+// CTAS = resident CTAs per SM the kernel is compiled for (register budget 65536 / (288 * CTAS)); input stages fill what is left of
+// the 227 KB of shared memory.
+template <class L, int CTAS>
+struct TileCfg {
+  static constexpr int kInBytes = L::Q * kTileRowBytes + kTileCells;  // q population rows + 512 bc ids
+  static constexpr int kMaxStages = (227 * 1024 / CTAS - 1024 - kTileBarBytes) / kInBytes;
+  static constexpr int kInStages = kMaxStages > 4 ? 4 : kMaxStages;
+  static constexpr int kSmemBytes = kTileBarBytes + kInStages * kInBytes;
+  static_assert(L::Q + 1 <= 32, "one producer lane per population + one for the ids");
+  static_assert(kInStages >= 2, "at least double buffering");
+};
+
+struct TileGeom {
+  int x, y0;       // plane and first row of the tile
+  unsigned cell0;  // element offset of its first cell inside a population
+};
+
+XLBN_DEVFN inline TileGeom tile_geom(const StepParams<__half>& p, int tile, int rows, int tiles_per_plane) {
+  TileGeom g;
+  g.x = p.x_begin + tile / tiles_per_plane;
+  g.y0 = (tile % tiles_per_plane) * rows;
+  g.cell0 = (unsigned)g.x * (unsigned)p.plane + (unsigned)g.y0 * (unsigned)p.nz;
+  return g;
+}
+
+// Where population l of a tile comes from: up to two contiguous runs (elements), in the order they are laid out in the stage row.
+template <class L>
+XLBN_DEVFN int tile_plan(const StepParams<__half>& p, int l, const TileGeom& g, int rows, const __half* (&src)[2], unsigned (&dst)[2], unsigned (&count)[2]) {
+  const int cx = L::ck(0, l), cy = L::ck(1, l);
+  const int tab = (cx == 1 && g.x == 0) ? 1 : ((cx == -1 && g.x == p.nx - 1) ? 2 : 0);  // ghost plane / periodic wrap in x (fill_step_params)
+  const __half* base = p.pull[tab][l] + (unsigned)g.x * (unsigned)p.plane;
+  const unsigned nz = (unsigned)p.nz;
+  const int ys = g.y0 - cy;  // first source row: pull from y - c_y (stream.py:66-78)
+  if (ys < 0) {  // row ny-1, then rows 0 .. rows-2
+    src[0] = base + (unsigned)(p.ny - 1) * nz;
+    dst[0] = 0;
+    count[0] = nz;
+    if (rows == 1) return 1;
+    src[1] = base;
+    dst[1] = nz;
+    count[1] = (unsigned)(rows - 1) * nz;
+    return 2;
+  }
+  if (ys + rows > p.ny) {  // rows ys .. ny-1, then row 0
+    int n = 0;
+    if (rows > 1) {
+      src[n] = base + (unsigned)ys * nz;
+      dst[n] = 0;
+      count[n] = (unsigned)(rows - 1) * nz;
+      ++n;
+    }
+    src[n] = base;
+    dst[n] = (unsigned)(rows - 1) * nz;
+    count[n] = nz;
+    return n + 1;
+  }
+  src[0] = base + (unsigned)ys * nz;
+  dst[0] = 0;
+  count[0] = (unsigned)rows * nz;
+  return 1;
+}
+
+// two half2 words -> (hi half of a, lo half of b): the pair one element to the right of a / to the left of b
+XLBN_DEV __half2 tile_funnel(uint32_t a, uint32_t b) {
+  uint32_t r;
+#if XLBN_ON_HOST
+  r = (a >> 16) | (b << 16);
+#else
+  asm("prmt.b32 %0, %1, %2, 0x5432;" : "=r"(r) : "r"(a), "r"(b));
+#endif
+  union {
+    uint32_t u;
+    __half2 h;
+  } c;
+  c.u = r;
+  return c.h;
+}
+XLBN_DEV uint32_t tile_bits(__half2 h) {
+  union {
+    __half2 h;
+    uint32_t u;
+  } c;
+  c.h = h;
+  return c.u;
+}
+
+// Thread t of a tile: its two cells' post-stream populations (as half2 words) and bc ids out of an input stage.
+template <class L>
+XLBN_DEV void tile_load(const StepParams<__half>& p, const uint32_t* in_words, const uint8_t* in_ids, const unsigned t, __half2 (&h)[L::Q], unsigned& ids) {
+  const unsigned nz = (unsigned)p.nz, z0 = (2u * t) & (nz - 1u);  // nz is a power of two (a divisor of 512)
+  const unsigned tp = (z0 == 0u) ? t + nz / 2u - 1u : t - 1u;          // word holding element z0 - 1 of the same row (periodic in z)
+  const unsigned tn = (z0 + 2u == nz) ? t + 1u - nz / 2u : t + 1u;     // word holding element z0 + 2
+  XLBN_FOR(L::Q, l)
+    constexpr int cz = L::ck(2, l);
+    const uint32_t w = in_words[l * kTileConsumers + t];
+    if constexpr (cz == 0) {
+      union {
+        uint32_t u;
+        __half2 h;
+      } c;
+      c.u = w;
+      h[l] = c.h;
+    } else if constexpr (cz == 1) {  // out[z] = in[z - 1]
+      h[l] = tile_funnel(in_words[l * kTileConsumers + tp], w);
+    } else {  // out[z] = in[z + 1]
+      h[l] = tile_funnel(w, in_words[l * kTileConsumers + tn]);
+    }
+  XLBN_END
+  ids = (unsigned)in_ids[2u * t] | ((unsigned)in_ids[2u * t + 1u] << 8);
+}
+
+// Collide the two cells and store; boundary cells as described at the top of the file.
+template <class L>
+XLBN_DEV void tile_compute(const StepParams<__half>& p, const __half2 (&h)[L::Q], const unsigned ids, const unsigned t, const TileGeom& g) {
+  using TS = __half;
+  constexpr int Q = L::Q;
+  const unsigned cell = g.cell0 + 2u * t;
+  const float omega = (float)p.omega;
+  const bool any_bc = ids != 0u;
+  auto put = [&](auto l_, uint32_t word) {
+    constexpr int l = decltype(l_)::value;
+    union {
+      uint32_t u;
+      Pack<TS, 2> a;
+    } c;
+    c.u = word;
+    gstore<TS, 2>(p.push[l] + cell, c.a);
+  };
+  if (!XLBN_ANY(0xffffffffu, any_bc)) {  // warp-uniform: no boundary cell in this warp
+    h2_collide_each<L>(h, omega, [&](auto l_, f32x2 out) { put(l_, tile_bits(__float22half2_rn(out.v))); });
+    return;
+  }
+  const int id0 = (int)(ids & 0xffu), id1 = (int)(ids >> 8);
+  const int k0 = id0 ? (int)p.kinds[id0] : 0, k1 = id1 ? (int)p.kinds[id1] : 0;
+  const bool complex_bc = (id0 == 255) | (id1 == 255) | (k0 != XLBN_BC_NONE && k0 != XLBN_BC_FULLWAY_BOUNCE_BACK && k0 != XLBN_BC_EQUILIBRIUM) |
+                          (k1 != XLBN_BC_NONE && k1 != XLBN_BC_FULLWAY_BOUNCE_BACK && k1 != XLBN_BC_EQUILIBRIUM);
+  // FullwayBounceBack halves: out[l] = f_post_stream[opp l], a bit copy (bc_fullway_bounce_back.py:60-72)
+  const uint32_t m = (k0 == XLBN_BC_FULLWAY_BOUNCE_BACK ? 0x0000ffffu : 0u) | (k1 == XLBN_BC_FULLWAY_BOUNCE_BACK ? 0xffff0000u : 0u);
+  h2_collide_each<L>(h, omega, [&](auto l_, f32x2 out) {
+    constexpr int l = decltype(l_)::value;
+    const uint32_t o = tile_bits(__float22half2_rn(out.v));
+    if (!complex_bc) put(l_, (o & ~m) | (tile_bits(h[L::opp(l)]) & m));
+  });
+  if (!any_bc) return;
+  if (!complex_bc) {  // EquilibriumBC halves: bc_equilibrium.py:76-86 followed by the ordinary collision = a per-BC constant (bc_precompute_kernel)
+    if (k0 == XLBN_BC_EQUILIBRIUM) {
+      const float* e = p.table[id0].eq_out;
+      XLBN_FOR(Q, l)
+        Pack<TS, 1> a;
+        a.v[0] = __float2half_rn(e[l]);
+        gstore<TS, 1>(p.push[l] + cell, a);
+      XLBN_END
+    }
+    if (k1 == XLBN_BC_EQUILIBRIUM) {
+      const float* e = p.table[id1].eq_out;
+      XLBN_FOR(Q, l)
+        Pack<TS, 1> a;
+        a.v[0] = __float2half_rn(e[l]);
+        gstore<TS, 1>(p.push[l] + (cell + 1u), a);
+      XLBN_END
+    }
+    return;
+  }
+  // every other kind, and cells with id 255 (not written: nse_stepper.py:356-358): the scalar boundary routine of the direct kernel
+  const unsigned nz = (unsigned)p.nz, j = 2u * t;
+  const int y = g.y0 + (int)(j / nz), z0 = (int)(j & (nz - 1u));
+  float fs[2][Q];
+  XLBN_FOR(Q, l)
+    const float2 f = __half22float2(h[l]);
+    fs[0][l] = f.x;
+    fs[1][l] = f.y;
+  XLBN_END
+  Pack<uint8_t, 2> pk;
+  pk.v[0] = (uint8_t)id0;
+  pk.v[1] = (uint8_t)id1;
+  bc_compute<L, XLBN_BGK, float, TS, 2>(p, pk, g.x, y, z0, fs);
+  if ((id0 == 255) | (id1 == 255)) store_cells<L, float, TS, 2, 0, true>(p, cell, pk, fs);
+  else store_cells<L, float, TS, 2, 0, false>(p, cell, pk, fs);
+}
+
+template <class L>
+bool tile_eligible(const StepParams<__half>& p, const void* f0, const void* f1, const void* ghost_lo, const void* ghost_hi, bool has_peers) {
+  auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % 16) == 0; };
+  if (has_peers || p.nz < 8 || p.nz > kTileCells || (kTileCells % p.nz) != 0 || (p.nz % 8) != 0) return false;
+  const int rows = kTileCells / p.nz;
+  if (p.ny % rows != 0) return false;
+  if (((long long)p.plane * 2) % 16 != 0) return false;  // ghost planes and population strides keep the 16-byte alignment
+  return aligned(f0) && aligned(f1) && aligned(ghost_lo) && aligned(ghost_hi) && aligned(p.bc);
+}
+
+#if !XLBN_ON_HOST
+// ---- device-only plumbing: mbarrier, bulk copies, named barrier -------------------------------------------------------------------
+namespace tile_ptx {
+__device__ __forceinline__ uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(saddr(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(saddr(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(saddr(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(saddr(dst_smem)), "l"(src), "r"(bytes), "r"(saddr(bar)) : "memory");
+}
+}  // namespace tile_ptx
+
+template <class L, int CTAS>
+__global__ void __launch_bounds__(kTileThreads, CTAS) step_tile_kernel(const __grid_constant__ StepParams<__half> p, const int n_tiles, const int rows, const int tiles_per_plane) {
+  using namespace tile_ptx;
+  using C = TileCfg<L, CTAS>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // one per input stage: the bulk copies of the stage have landed
+  uint64_t* empty = full + C::kInStages;                // one per input stage: all 8 consumer warps have taken their words
+  unsigned char* in0 = smem + kTileBarBytes;
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < C::kInStages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, kTileConsumers / 32);
+    }
+    mbar_init_fence();
+  }
+  __syncthreads();
+
+  if (warp == kTileConsumers / 32) {
+    // ---- producer: runs ahead of the consumers by up to kInStages tiles ----
+    int k = 0;
+    for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++k) {
+      const int s = k % C::kInStages;
+      const uint32_t phase = (uint32_t)(k / C::kInStages) & 1u;
+      mbar_wait(empty + s, phase ^ 1u);  // first round: passes at once
+      const TileGeom g = tile_geom(p, tile, rows, tiles_per_plane);
+      unsigned char* stage = in0 + s * C::kInBytes;
+      if (lane == 0) mbar_expect_tx(full + s, (uint32_t)C::kInBytes);
+      __syncwarp();
+      if (lane < L::Q) {
+        const __half* src[2];
+        unsigned dst[2], count[2];
+        const int n = tile_plan<L>(p, lane, g, rows, src, dst, count);
+        for (int i = 0; i < n; ++i) bulk_load(stage + lane * kTileRowBytes + dst[i] * 2u, src[i], count[i] * 2u, full + s);
+      } else if (lane == L::Q) {
+        bulk_load(stage + L::Q * kTileRowBytes, p.bc + g.cell0, kTileCells, full + s);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers: 8 independent warps, no CTA-wide synchronisation ----
+  const unsigned t = (unsigned)tid;
+  int k = 0;
+  for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++k) {
+    const int s = k % C::kInStages;
+    const uint32_t phase = (uint32_t)(k / C::kInStages) & 1u;
+    const TileGeom g = tile_geom(p, tile, rows, tiles_per_plane);
+    const unsigned char* stage = in0 + s * C::kInBytes;
+    __half2 h[L::Q];
+    unsigned ids;
+    mbar_wait(full + s, phase);
+    tile_load<L>(p, reinterpret_cast<const uint32_t*>(stage), stage + L::Q * kTileRowBytes, t, h, ids);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);  // the stage can be refilled while this tile is computed
+    tile_compute<L>(p, h, ids, t, g);
+  }
+}
+
+template <class L, int CTAS>
+int launch_step_tile(const StepParams<__half>& p, int x_count, cudaStream_t stream) {
+  using C = TileCfg<L, CTAS>;
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    XLBN_CUDA_OK(cudaGetDevice(&dev));
+    XLBN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    XLBN_CUDA_OK(cudaFuncSetAttribute(step_tile_kernel<L, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  }
+  const int rows = kTileCells / p.nz, tiles_per_plane = p.ny / rows;
+  const long long n_tiles = (long long)tiles_per_plane * x_count;
+  if (n_tiles > 0x7fffffffLL) return fail(XLBN_E_SHAPE, "tile kernel: %lld tiles", n_tiles);
+  const long long resident = (long long)CTAS * sm_count;
+  const int grid = (int)(n_tiles < resident ? n_tiles : resident);  // persistent: CTAS CTAs per SM walk the tiles round-robin
+  step_tile_kernel<L, CTAS><<<grid, kTileThreads, C::kSmemBytes, stream>>>(p, (int)n_tiles, rows, tiles_per_plane);
+  XLBN_LAUNCH_OK("step_tile_kernel launch");
+  return 0;
+}
+#endif  // !XLBN_ON_HOST
+
+}  // namespace xlbn

@@ -69,8 +69,6 @@ class PeerHalo:
     """Device-resident ghost planes of one slab, connected to the ring neighbours through CUDA IPC."""
 
     def __init__(self, grid, velocity_set, precision_policy, dims, group=None):
-        if velocity_set.d != 3:
-            raise NotImplementedError("x-slab decomposition is implemented for 3-D lattices")
         self.rank, self.world = grid.rank, grid.nDevices
         self.group = group
         self.device = grid.device

@@ -82,7 +82,7 @@ SIGNATURES = {
     "xlbn_stepper_prepare": [_P, _D, _P],
     "xlbn_step": [_P, _P, _P, _P, _P, C.POINTER(Domain), _D, _I, _P, _P],
     "xlbn_mask_indices": [_I, _I, _P, _LL, _I, _I, Int3, Int3, Int3, _P, _P, _P, _P],
-    "xlbn_mask_finalize_jax": [_I, Int3, Int3, Int3, _P, _P, _P],
+    "xlbn_mask_finalize_jax": [_I, Int3, Int3, Int3, _P, _P, _P, _P],
     "xlbn_mask_mesh": [_I, _P, _LL, _I, _I, Int3, _P, _P, _P, _P],
     "xlbn_pack_missing": [_I, _P, _P, _LL, _P],
     "xlbn_stream": [_I, _P, _P, _I, Int3, _P],

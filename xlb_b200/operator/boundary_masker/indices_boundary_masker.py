@@ -45,8 +45,10 @@ class IndicesBoundaryMasker(Operator):
         stream = native.stream_of(bc_mask)
         L = native.lib()
 
-        solid = None
+        solid = incoming = None
         if mode == native.MASK_JAX:
+            if bool(missing_mask.any()):  # entries set by an earlier masker are streamed along, as the reference does (L56-63, 92)
+                incoming = missing_mask.clone()
             solid = torch.zeros((local[0] + 2) * (local[1] + 2) * (local[2] + 2), dtype=torch.uint8, device=bc_mask.device)
         for bc in bclist:
             assert bc.indices is not None, f'Please specify indices associated with the {bc.__class__.__name__} BC using keyword "indices"!'
@@ -71,7 +73,8 @@ class IndicesBoundaryMasker(Operator):
             )  # fmt: skip
         if mode == native.MASK_JAX:
             native.check(
-                L.xlbn_mask_finalize_jax(self._lattice, native.int3(gshape), native.int3(start), native.int3(local), native.ptr(missing_mask), native.ptr(solid), stream)
+                L.xlbn_mask_finalize_jax(self._lattice, native.int3(gshape), native.int3(start), native.int3(local), native.ptr(missing_mask), native.ptr(solid),
+                                         native.ptr(incoming), stream)
             )
         return bc_mask, missing_mask
 
