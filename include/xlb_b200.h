@@ -99,7 +99,10 @@ typedef struct xlbn_stepper_desc {
                                301 = KBC only: register-lean formulation of the collision, one cell per thread (same algebra
                                      as kbc.py:268-296, feq recomputed per pass instead of held; rounding-level differences).
                                      This is what 0 selects for an unforced KBC stepper.
-                               300 = KBC only: the literal three-array formulation, one cell per thread */
+                               300 = KBC only: the literal three-array formulation with the reference's own roundings (IEEE divisions,
+                                     nothing fused): bit-identical to the reference kernel; the parity form, ~2x slower
+                               402 / 403 = FP32FP16 BGK only: the persistent TMA-fed tile kernel with 2 / 3 CTAs per SM (csrc/step_tile.cuh);
+                                     needs nz | 512, nz % 8 == 0, ny % (512 / nz) == 0, no halo handle on the call */
   const xlbn_bc_desc* bcs;  /* n_bc entries, copied */
 } xlbn_stepper_desc;
 

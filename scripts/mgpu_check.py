@@ -35,7 +35,12 @@ def build(case, shape, lattice, policy, collision, distributed):
     xlb.init(velocity_set=vs, default_backend=be, default_precision_policy=pp)
     grid = grid_factory(shape, distributed=distributed)
     box, bne = grid.bounding_box_indices(), grid.bounding_box_indices(remove_edges=True)
-    if case == "cavity":
+    if case == "cavity2d":  # examples/cfd/lid_driven_cavity_2d(_distributed).py: Halfway walls, EquilibriumBC lid
+        walls = [box["bottom"][i] + box["left"][i] + box["right"][i] for i in range(2)]
+        walls = np.unique(np.array(walls), axis=-1).tolist()
+        bcs = [EquilibriumBC(rho=1.0, u=(0.05, 0.0), indices=bne["top"]), HalfwayBounceBackBC(indices=walls)]
+        omega = 1.5
+    elif case == "cavity":
         walls = [box["bottom"][i] + box["left"][i] + box["right"][i] + box["front"][i] + box["back"][i] for i in range(3)]
         walls = np.unique(np.array(walls), axis=-1).tolist()
         bcs = [EquilibriumBC(rho=1.0, u=(0.02, 0.0, 0.0), indices=bne["top"]), FullwayBounceBackBC(indices=walls)]
@@ -97,6 +102,9 @@ def main():
         ("periodic", (8 * world, 16, 32), "D3Q27", "FP32FP16", "BGK", 15),
         ("sphere", (24 * world, 24, 24), "D3Q27", "FP32FP32", "KBC", 25),
         ("sphere", (24 * world, 24, 24), "D3Q19", "FP64FP32", "BGK", 25),
+        ("cavity2d", (16 * world, 40), "D2Q9", "FP32FP32", "BGK", 40),
+        ("cavity2d", (16 * world, 40), "D2Q9", "FP32FP32", "KBC", 40),
+        ("cavity", (8 * world, 16, 64), "D3Q19", "FP32FP16", "BGK", 25),  # tile-kernel shape (nz | 512): interior planes take the tile path
     ]
     for case, shape, lattice, policy, collision, steps in cases:
         f, bc, mm = run(case, shape, lattice, policy, collision, steps, None)

@@ -98,13 +98,15 @@ int host_step_tile(const StepCall& c) {
   using C = TileCfg<L, 2>;
   const int rows = kTileCells / p.nz, tiles_per_plane = p.ny / rows, n_tiles = tiles_per_plane * c.x_count;
   static unsigned char in[C::kInBytes];
+  static TileEqTable eq;
+  tile_eq_table_fill<L>(p, eq);  // the kernel's prologue (one thread per CTA)
   for (int tile = 0; tile < n_tiles; ++tile) {
     const TileGeom g = tile_geom(p, tile, rows, tiles_per_plane);
     memset(in, 0xff, sizeof(in));
     for (int l = 0; l < L::Q; ++l) {  // the producer warp, lane l
       const __half* src[2];
       unsigned dst[2], count[2];
-      const int n = tile_plan<L>(p, l, g, rows, src, dst, count);
+      const int n = tile_plan<L>(p, l, L::ck(0, l), L::ck(1, l), g, rows, src, dst, count);
       unsigned total = 0;
       for (int i = 0; i < n; ++i) {
         if ((reinterpret_cast<uintptr_t>(src[i]) % 16) || ((dst[i] * 2u) % 16) || ((count[i] * 2u) % 16)) return fail(XLBN_E_SHAPE, "mirror: bulk copy not 16-byte aligned");
@@ -118,7 +120,7 @@ int host_step_tile(const StepCall& c) {
       __half2 h[L::Q];
       unsigned ids;
       tile_load<L>(p, reinterpret_cast<const uint32_t*>(in), in + L::Q * kTileRowBytes, t, h, ids);
-      tile_compute<L>(p, h, ids, t, g);
+      tile_compute<L>(p, eq, h, ids, t, g);
     }
   }
   return 0;

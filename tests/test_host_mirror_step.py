@@ -29,7 +29,7 @@ COLLISION = {"BGK": 0, "KBC": 1, "SmagorinskyLESBGK": 2}
 DTYPE = {np.dtype(np.float16): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}
 # (lattice, collision code) pairs the library instantiates: base | 4 = forced (XLBN_COLLISION_FORCED), | 8 = lean KBC (kLeanKbc)
 PARTS = [("D3Q19", 0), ("D3Q19", 4), ("D3Q19", 2), ("D3Q19", 6), ("D3Q27", 0), ("D3Q27", 1), ("D3Q27", 4), ("D3Q27", 5), ("D3Q27", 2), ("D3Q27", 6),
-         ("D3Q27", 9), ("D2Q9", 0), ("D2Q9", 1), ("D2Q9", 4), ("D2Q9", 5), ("D2Q9", 9), ("D2Q9X", 0), ("D2Q9X", 1)]  # fmt: skip
+         ("D3Q27", 9), ("D2Q9", 0), ("D2Q9", 1), ("D2Q9", 4), ("D2Q9", 5), ("D2Q9", 9), ("D2Q9X", 0), ("D2Q9X", 1), ("D3Q27", 17), ("D2Q9", 17)]  # fmt: skip
 SYM = lambda lat, coll: f"mirror_step_{'0x' if lat == 'D2Q9X' else LATTICE[lat]}_{coll}"  # noqa: E731
 
 
@@ -66,7 +66,7 @@ def mirror():
     return lib
 
 
-def mirror_run(lib, g, steps=None, v=1, lean_kbc=False, masks=None, slab_axes=False):
+def mirror_run(lib, g, steps=None, v=1, lean_kbc=False, masks=None, slab_axes=False, exact_kbc=False):
     """The user loop (step, swap) through the host-compiled kernel source; masks and aux data from the oracle helpers
     (or `masks` = (lat, bcs, bc_mask, missing) built by the caller)."""
     lat, bcs, bc_mask, missing = masks if masks is not None else oracle_masks(g, "warp")
@@ -83,7 +83,7 @@ def mirror_run(lib, g, steps=None, v=1, lean_kbc=False, masks=None, slab_axes=Fa
     shape = g["shape"]
     # 2-D: kernel extents (1, nx, ny); with slab_axes the x-slab axis order (nx, 1, ny) of csrc/lattice.cuh D2Q9X
     dims = (C.c_int32 * 3)(*(((shape[0], 1, shape[1]) if slab_axes else (1,) + tuple(shape)) if lat.d == 2 else tuple(shape)))
-    coll = COLLISION[g["collision"]] | (4 if g["force_vector"] is not None else 0) | (8 if lean_kbc else 0)  # 8: csrc/lbm_math.cuh kLeanKbc
+    coll = COLLISION[g["collision"]] | (4 if g["force_vector"] is not None else 0) | (8 if lean_kbc else 0) | (16 if exact_kbc else 0)  # csrc/lbm_math.cuh kLeanKbc, kExactKbc
     force = np.zeros(3)
     if g["force_vector"] is not None:
         force[: lat.d] = g["force_vector"]
@@ -307,3 +307,15 @@ def test_2d_slab_axis_order_gives_the_same_bits(mirror, name):
     against the ordinary 2-D order (1, nx, ny): identical populations, BC normals and outflow neighbour reads included."""
     g = load_golden(name)
     assert np.array_equal(mirror_run(mirror, g, slab_axes=True), mirror_run(mirror, g))
+
+
+@pytest.mark.parametrize("name", [n for n in STEP_CASES + LATE_CASES + WARP_CASES if "kbc" in n and "fp16" not in n])
+def test_literal_kbc_with_the_references_roundings_is_bit_identical(mirror, name):
+    """cells_per_thread = 300 (kExactKbc): the literal KBC formulation with IEEE divisions and nothing fused reproduces the C restatement
+    of the reference kernel bit for bit — the fast forms (lean default, reciprocal-based literal) are held to the 1e-5 tolerance."""
+    from common import c_oracle_run
+
+    g = load_golden(name)
+    ref, _, _ = c_oracle_run(g)
+    f = mirror_run(mirror, g, exact_kbc=True)
+    assert np.array_equal(f, ref), f"{int((f != ref).sum())} of {f.size} values differ, rel err {rel_err(f, ref):.3e}"

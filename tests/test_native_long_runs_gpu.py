@@ -123,8 +123,8 @@ def test_c3_sphere_d3q27_kbc_256x64x64_1000_steps(v):
     g, lat, bc_mask, missing, ref = sphere_reference()
     f, bm, mm = native_run(g, cells_per_thread=v)
     assert np.array_equal(bm, bc_mask) and np.array_equal(mm, missing), "masks must be bit-exact"
-    # populations and density at the north-star 1e-5.  The velocity is a DIFFERENCE of populations 25x smaller than they are (u_max = 0.04
-    # against f ~ 1): the same absolute agreement reads 25x larger when quoted relative to u_max — measured 1.7e-5 (= 7e-7 in lattice
-    # units) for both KBC formulations, whose reciprocal-based divisions and explicit fused operations differ from the C oracle's
-    # roundings (the BGK chain, which does not, is bit-identical after 1000 steps).  Gate: 5e-5 of u_max.
-    compare(f"C3 sphere 256x64x64 D3Q27 KBC v={v}", f, ref, lat, 1e-5, 0.04, u_tol=5e-5)
+    # v = 300, the literal formulation with the reference's own roundings, must be BIT-IDENTICAL after 1000 steps.  The lean default
+    # (reciprocal-based divisions, explicit fused operations) is held to the north-star 1e-5 on populations and density; its velocity —
+    # a DIFFERENCE of populations 25x smaller than they are (u_max = 0.04 against f ~ 1) — agrees to 7e-7 in lattice units, which
+    # reads 1.7e-5 when quoted relative to u_max: gate 5e-5 of u_max.
+    compare(f"C3 sphere 256x64x64 D3Q27 KBC v={v}", f, ref, lat, 1e-5, 0.04, u_tol=5e-5, exact=(v == 300))

@@ -99,3 +99,39 @@ def test_2d_slab_run_is_bit_identical(name, n_slabs, split_faces):
     whole, _, _ = native_run(g, steps=steps)
     parts = run_slabs(g, n_slabs, steps, split_faces)
     assert np.array_equal(parts, whole)
+
+
+def test_a_dead_neighbour_is_a_loud_error():
+    """A slab whose ring neighbour never signals: the device-side wait gives up after the time-out (never hanging the GPU), marks the handle in
+    mapped host memory, and every later call on the handle — xlbn_step with the halo, push, signal, wait — fails with XLBN_E_STATE instead
+    of stepping on stale ghost planes (round 1 let the run continue silently)."""
+    g = load_golden("cavity_d3q19_bgk_fp32")
+    stepper, f_0, f_1, bc_mask, missing_mask = native_case(g)
+    handle = stepper._native_handle()
+    L = native.lib()
+    nx, ny, nz = g["shape"]
+    st = native.stream_of(f_0)
+    halos, bases = [], []
+    for _ in range(2):
+        h = C.c_void_p()
+        native.check(L.xlbn_halo_create(stepper._lattice, stepper.precision_policy.store_precision.code, ny, nz, C.byref(h)))
+        p, nbytes = C.c_void_p(), C.c_longlong()
+        native.check(L.xlbn_halo_ghost_ptr(h, C.byref(p), C.byref(nbytes)))
+        halos.append(h)
+        bases.append(p.value)
+    for i, h in enumerate(halos):
+        other = C.create_string_buffer(np.uint64(bases[1 - i]).tobytes(), 64)
+        native.check(L.xlbn_halo_connect(h, other, other, 1))
+        native.check(L.xlbn_halo_set_timeout(h, 0.2))
+    assert L.xlbn_halo_timed_out(halos[0]) == 0
+    native.check(L.xlbn_halo_wait(halos[0], 7, st))  # nobody ever signals step 7
+    torch.cuda.synchronize()
+    assert L.xlbn_halo_timed_out(halos[0]) == 1 and L.xlbn_halo_timed_out(halos[1]) == 0
+    dom = native.Domain(nx, ny, nz, 0, nx)
+    rc = L.xlbn_step(handle, native.ptr(f_0), native.ptr(f_1), native.ptr(bc_mask), None, C.byref(dom), 1.0, 7, halos[0], st)
+    assert rc == -5 and b"did not deliver" in L.xlbn_last_error()  # XLBN_E_STATE
+    assert L.xlbn_halo_signal(halos[0], 8, st) == -5 and L.xlbn_halo_wait(halos[0], 8, st) == -5
+    native.check(L.xlbn_step(handle, native.ptr(f_0), native.ptr(f_1), native.ptr(bc_mask), None, C.byref(dom), 1.0, 7, None, st))  # without the halo: fine
+    torch.cuda.synchronize()
+    for h in halos:
+        L.xlbn_halo_destroy(h)

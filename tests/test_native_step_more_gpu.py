@@ -24,7 +24,11 @@ def is_exact_case(g, v):
     """BGK with the default / scalar / half2-state paths takes the reference's fp32 (fp64) roundings one by one (csrc/lbm_math.cuh
     "ROUNDINGS"): those runs must reproduce the C restatement of the reference's fused Warp kernel BIT FOR BIT.  (The packed fp32x2
     variants 102 / 104 use reciprocal-based division, KBC uses explicit fused operations: tolerance only.)"""
-    return g["collision"] == "BGK" and g.get("force_vector") is None and v in (0, 1, 2, 4, 8, 202, 203)
+    if g.get("force_vector") is not None:
+        return False
+    if g["collision"] == "KBC":
+        return v == 300  # the literal formulation with the reference's roundings (kExactKbc); the lean default is tolerance-only
+    return g["collision"] == "BGK" and v in (0, 1, 2, 4, 8, 202, 203, 402, 403)
 
 
 def check_step_case(name, backend, v=0):

@@ -43,11 +43,11 @@ def test_reference_flow_past_sphere_script(tmp_path):
     outflow, Halfway sphere, Fullway walls, 10 000 steps with post-processing (JAX-convention Macroscopic + save_image) every 1 000."""
     out = run_script("cfd/flow_past_sphere_3d.py", [], tmp_path)
     assert "Completed step 9999" in out, out[-1500:]
-    assert len([f for f in os.listdir(tmp_path) if f.endswith(".png")]) >= 10
+    assert len([f for f in os.listdir(tmp_path) if f.endswith((".png", ".pgm"))]) >= 10  # save_image: this library writes PGM (no matplotlib)
 
 
 def test_reference_lid_driven_cavity_2d_script(tmp_path):
     """examples/cfd/lid_driven_cavity_2d.py as shipped: 500x500 D2Q9 BGK, Halfway walls + EquilibriumBC lid, 50 000 steps, VTK + PNG output."""
     run_script("cfd/lid_driven_cavity_2d.py", [], tmp_path, timeout=1500)
     files = os.listdir(tmp_path)
-    assert any(f.endswith(".vtk") or f.endswith(".vti") or f.endswith(".vtr") for f in files) and any(f.endswith(".png") for f in files), files
+    assert any(f.endswith(".vtk") or f.endswith(".vti") or f.endswith(".vtr") for f in files) and any(f.endswith((".png", ".pgm")) for f in files), files

@@ -33,7 +33,18 @@ def _binary(name, tname=None):
 
 
 numpy = types.ModuleType("jax.numpy")
-numpy.ndarray = _torch.Tensor  # `isinstance(field, jnp.ndarray)` is true for device fields
+class _JaxArrayMeta(type):
+    def __instancecheck__(cls, x):  # device fields are "jax arrays" unless they were created on the WARP convention (a wp.array is not)
+        from xlb_b200.field import WarpField
+
+        return isinstance(x, _torch.Tensor) and not isinstance(x, WarpField)
+
+
+class _JaxArray(metaclass=_JaxArrayMeta):
+    pass
+
+
+numpy.ndarray = _JaxArray
 for _n in ("sqrt", "abs", "sin", "cos", "exp", "log", "square", "isnan", "zeros_like", "ones_like"):
     setattr(numpy, _n, _unary(_n))
 for _n in ("maximum", "minimum"):

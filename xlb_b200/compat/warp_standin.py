@@ -76,7 +76,10 @@ sqrt, sin, cos, exp, log, floor, ceil, pow = np.sqrt, np.sin, np.cos, np.exp, np
 
 
 def to_jax(a):
-    return a
+    """wp.to_jax(field): the same memory seen as a JAX-convention array."""
+    from xlb_b200.field import Field, WarpField
+
+    return a.as_subclass(Field) if isinstance(a, WarpField) else a
 
 
 def from_jax(a, dtype=None):

@@ -57,6 +57,8 @@ template <> int dispatch_step<D2Q9, XLBN_BGK | kF>(const StepCall&);
 template <> int dispatch_step<D2Q9, XLBN_KBC | kF>(const StepCall&);
 template <> int dispatch_step<D3Q27, XLBN_KBC | kLeanKbc>(const StepCall&);  // tuning variant (cells_per_thread = 301)
 template <> int dispatch_step<D2Q9, XLBN_KBC | kLeanKbc>(const StepCall&);
+template <> int dispatch_step<D3Q27, XLBN_KBC | kExactKbc>(const StepCall&);  // parity form (cells_per_thread = 300)
+template <> int dispatch_step<D2Q9, XLBN_KBC | kExactKbc>(const StepCall&);
 template <> int dispatch_step<D2Q9X, XLBN_BGK>(const StepCall&);  // 2-D x-slab axis order (step_inst_d2q9x.cu)
 template <> int dispatch_step<D2Q9X, XLBN_KBC>(const StepCall&);
 template <> int dispatch_step<D2Q9X, XLBN_KBC | kLeanKbc>(const StepCall&);
@@ -258,7 +260,8 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
   if (s->cells_per_thread == 301 && s->forced) return fail(XLBN_E_UNSUPPORTED, "xlbn_step: the lean KBC variant (cells_per_thread = 301) has no forced form");
   // KBC: the register-lean formulation is the default (B200: 0.81 vs 0.69 of the HBM roofline, profiles/r2_*); 300 = literal
   const bool lean = s->collision == XLBN_KBC && !s->forced && (s->cells_per_thread == 0 || s->cells_per_thread == 301);
-  const int coll = s->collision | (s->forced ? kF : 0) | (lean ? kLeanKbc : 0);
+  const bool exact_kbc = s->collision == XLBN_KBC && !s->forced && s->cells_per_thread == 300 && !slab_2d;
+  const int coll = s->collision | (s->forced ? kF : 0) | (lean ? kLeanKbc : 0) | (exact_kbc ? kExactKbc : 0);
   switch (s->lattice) {
     case XLBN_D3Q19:
       switch (coll) {
@@ -275,6 +278,7 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
         case XLBN_BGK | kF: return dispatch_step<D3Q27, XLBN_BGK | kF>(c);
         case XLBN_KBC | kF: return dispatch_step<D3Q27, XLBN_KBC | kF>(c);
         case XLBN_KBC | kLeanKbc: return dispatch_step<D3Q27, XLBN_KBC | kLeanKbc>(c);
+        case XLBN_KBC | kExactKbc: return dispatch_step<D3Q27, XLBN_KBC | kExactKbc>(c);
         case XLBN_SMAGORINSKY_LES_BGK: return dispatch_step<D3Q27, XLBN_SMAGORINSKY_LES_BGK>(c);
         case XLBN_SMAGORINSKY_LES_BGK | kF: return dispatch_step<D3Q27, XLBN_SMAGORINSKY_LES_BGK | kF>(c);
       }
@@ -294,6 +298,7 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
         case XLBN_BGK | kF: return dispatch_step<D2Q9, XLBN_BGK | kF>(c);
         case XLBN_KBC | kF: return dispatch_step<D2Q9, XLBN_KBC | kF>(c);
         case XLBN_KBC | kLeanKbc: return dispatch_step<D2Q9, XLBN_KBC | kLeanKbc>(c);
+        case XLBN_KBC | kExactKbc: return dispatch_step<D2Q9, XLBN_KBC | kExactKbc>(c);
       }
       break;
   }

@@ -138,16 +138,21 @@ XLBN_DEV void collide_kbc(const TC (&f)[L::Q], const TC (&feq)[L::Q], TC rho, TC
   TC sp1 = TC(0), sp2 = TC(0);
   XLBN_FOR(L::Q, l)
     const TC dh = fneq[l] - ds[l];
-    TC temp;
-    if constexpr (FAST) temp = dh * rcp_approx_(feq[l]);
-    else temp = dh / feq[l];
-    sp1 = fma_(temp, ds[l], sp1);
-    sp2 = fma_(temp, dh, sp2);
+    if constexpr (FAST) {
+      const TC temp = dh * rcp_approx_(feq[l]);
+      sp1 = fma_(temp, ds[l], sp1);
+      sp2 = fma_(temp, dh, sp2);
+    } else {  // the reference's roundings, one per operation (kbc.py:284-291)
+      const TC temp = dh / feq[l];
+      sp1 = sp1 + temp * ds[l];
+      sp2 = sp2 + temp * dh;
+    }
   XLBN_END
   const TC gamma = inv_beta - (TC(2.0) - inv_beta) * sp1 / (TC(1e-32) + sp2);
   XLBN_FOR(L::Q, l)
     const TC dh = fneq[l] - ds[l];
-    out[l] = fma_(-beta, fma_(gamma, dh, TC(2.0) * ds[l]), f[l]);
+    if constexpr (FAST) out[l] = fma_(-beta, fma_(gamma, dh, TC(2.0) * ds[l]), f[l]);
+    else out[l] = f[l] - beta * (TC(2.0) * ds[l] + gamma * dh);  // kbc.py:294-296
   XLBN_END
 }
 
@@ -212,6 +217,9 @@ XLBN_DEV void exact_difference(TC rho, const TC (&u)[L::D], const TC (&feq)[L::Q
 // against 80 / 1 KiB for collide_kbc, for +9 % instructions (profiles/round2_prep/).  Differs from collide_kbc by rounding
 // only (x/4 -> x*0.25 is exact; the output is f - beta*gamma*fneq - beta*(2-gamma)*ds instead of f - beta*(2 ds + gamma dh)).
 constexpr int kLeanKbc = 8;  // internal flag or-ed onto XLBN_KBC in the COLL template argument
+// cells_per_thread = 300: the literal KBC formulation with the reference's roundings (IEEE divisions, nothing fused): bit-identical to
+// the reference kernel, ~35 divisions per cell (the parity form; the lean form above is the fast default)
+constexpr int kExactKbc = 16;
 
 XLBN_DEV void launder(float& x) {
 #if !XLBN_ON_HOST

@@ -204,7 +204,7 @@ XLBN_DEV void gstore(T* p, const Pack<T, V>& x) {
 
 // FAST (reciprocal-based) divisions where the kernel is issue-bound: single-precision KBC.  fp64 and BGK keep IEEE division.
 template <int COLL, class TC>
-constexpr bool kFast = (kBaseCollision<COLL> == XLBN_KBC) && (sizeof(TC) == 4);
+constexpr bool kFast = (kBaseCollision<COLL> == XLBN_KBC) && (sizeof(TC) == 4) && (COLL & kExactKbc) == 0;
 
 // BGK / KBC take the two-argument form they were tuned and validated with; SmagorinskyLESBGK and every forced operator
 // read their extra constants from the parameter block.
@@ -838,6 +838,9 @@ int launch_step_base(const StepParams<TS>& p, int x_count, int requested_v, cons
   constexpr bool can_h2 = sizeof(TC) == 4 && sizeof(TS) == 2 && COLL == XLBN_BGK;
   if (req == 0) req = can_h2 ? 202 : 1;
 #if !XLBN_ON_HOST
+  if constexpr (can_h2 && L::D == 3) {  // FP32FP16 BGK default: the tile kernel wherever the slab can be tiled (B200: 0.82 vs 0.69 of the roofline)
+    if (requested_v == 0 && tile_eligible<L>(p, f0, f1, g0, g1, o0 != nullptr || o1 != nullptr)) req = 402;
+  }
   if (req == 402 || req == 403) {  // the tile kernel (step_tile.cuh), explicitly: 402 = two CTAs per SM, 403 = three (D3Q19)
     if constexpr (can_h2 && L::D == 3) {
       if (!tile_eligible<L>(p, f0, f1, g0, g1, o0 != nullptr || o1 != nullptr))

@@ -34,15 +34,42 @@ constexpr int kTileConsumers = 256;               // consumer threads = half2 wo
 constexpr int kTileThreads = kTileConsumers + 32;  // + the producer warp
 constexpr int kTileRowBytes = kTileCells * 2;
 constexpr int kTileBarBytes = 128;
+XLBN_DEV uint32_t tile_bits(__half2 h);
+constexpr int kTileEqSlots = 4;  // EquilibriumBC ids whose constant update is kept in shared memory (more: those cells take the scalar routine)
+
+// Per-CTA copy of the EquilibriumBC constants (BcEntry::eq_out, refreshed by bc_precompute_kernel when omega changes): slot_of[id] =
+// slot of a boundary id or 0xff, word[slot][l] = the update of population l as a half2 word (e, e).
+struct TileEqTable {
+  uint32_t word[kTileEqSlots][kMaxQ];
+  uint8_t slot_of[256];
+};
+
+template <class L>
+XLBN_DEV void tile_eq_table_fill(const StepParams<__half>& p, TileEqTable& tab) {  // one thread
+  int n = 0;
+  for (int id = 0; id < 256; ++id) {
+    tab.slot_of[id] = 0xff;
+    if (id == 0 || id == 255 || p.kinds[id] != XLBN_BC_EQUILIBRIUM || n == kTileEqSlots) continue;
+    tab.slot_of[id] = (uint8_t)n;
+    for (int l = 0; l < L::Q; ++l) {
+      const __half e = __float2half_rn(p.table[id].eq_out[l]);
+      tab.word[n][l] = tile_bits(__halves2half2(e, e));
+    }
+    ++n;
+  }
+  for (; n < kTileEqSlots; ++n)
+    for (int l = 0; l < L::Q; ++l) tab.word[n][l] = 0u;
+}
 
 // CTAS = resident CTAs per SM the kernel is compiled for (register budget 65536 / (288 * CTAS)); input stages fill what is left of
 // the 227 KB of shared memory.
 template <class L, int CTAS>
 struct TileCfg {
   static constexpr int kInBytes = L::Q * kTileRowBytes + kTileCells;  // q population rows + 512 bc ids
-  static constexpr int kMaxStages = (227 * 1024 / CTAS - 1024 - kTileBarBytes) / kInBytes;
+  static constexpr int kFixedBytes = kTileBarBytes + (int)((sizeof(TileEqTable) + 127) / 128 * 128);
+  static constexpr int kMaxStages = (227 * 1024 / CTAS - 1024 - kFixedBytes) / kInBytes;
   static constexpr int kInStages = kMaxStages > 4 ? 4 : kMaxStages;
-  static constexpr int kSmemBytes = kTileBarBytes + kInStages * kInBytes;
+  static constexpr int kSmemBytes = kFixedBytes + kInStages * kInBytes;
   static_assert(L::Q + 1 <= 32, "one producer lane per population + one for the ids");
   static_assert(kInStages >= 2, "at least double buffering");
 };
@@ -61,9 +88,9 @@ XLBN_DEVFN inline TileGeom tile_geom(const StepParams<__half>& p, int tile, int 
 }
 
 // Where population l of a tile comes from: up to two contiguous runs (elements), in the order they are laid out in the stage row.
+// (cx, cy) = kernel-axis velocity components of population l: the producer lane looks them up once, before its tile loop.
 template <class L>
-XLBN_DEVFN int tile_plan(const StepParams<__half>& p, int l, const TileGeom& g, int rows, const __half* (&src)[2], unsigned (&dst)[2], unsigned (&count)[2]) {
-  const int cx = L::ck(0, l), cy = L::ck(1, l);
+XLBN_DEVFN int tile_plan(const StepParams<__half>& p, int l, int cx, int cy, const TileGeom& g, int rows, const __half* (&src)[2], unsigned (&dst)[2], unsigned (&count)[2]) {
   const int tab = (cx == 1 && g.x == 0) ? 1 : ((cx == -1 && g.x == p.nx - 1) ? 2 : 0);  // ghost plane / periodic wrap in x (fill_step_params)
   const __half* base = p.pull[tab][l] + (unsigned)g.x * (unsigned)p.plane;
   const unsigned nz = (unsigned)p.nz;
@@ -148,7 +175,7 @@ XLBN_DEV void tile_load(const StepParams<__half>& p, const uint32_t* in_words, c
 
 // Collide the two cells and store; boundary cells as described at the top of the file.
 template <class L>
-XLBN_DEV void tile_compute(const StepParams<__half>& p, const __half2 (&h)[L::Q], const unsigned ids, const unsigned t, const TileGeom& g) {
+XLBN_DEV void tile_compute(const StepParams<__half>& p, const TileEqTable& eq, const __half2 (&h)[L::Q], const unsigned ids, const unsigned t, const TileGeom& g) {
   using TS = __half;
   constexpr int Q = L::Q;
   const unsigned cell = g.cell0 + 2u * t;
@@ -169,35 +196,31 @@ XLBN_DEV void tile_compute(const StepParams<__half>& p, const __half2 (&h)[L::Q]
   }
   const int id0 = (int)(ids & 0xffu), id1 = (int)(ids >> 8);
   const int k0 = id0 ? (int)p.kinds[id0] : 0, k1 = id1 ? (int)p.kinds[id1] : 0;
-  const bool complex_bc = (id0 == 255) | (id1 == 255) | (k0 != XLBN_BC_NONE && k0 != XLBN_BC_FULLWAY_BOUNCE_BACK && k0 != XLBN_BC_EQUILIBRIUM) |
-                          (k1 != XLBN_BC_NONE && k1 != XLBN_BC_FULLWAY_BOUNCE_BACK && k1 != XLBN_BC_EQUILIBRIUM);
-  // FullwayBounceBack halves: out[l] = f_post_stream[opp l], a bit copy (bc_fullway_bounce_back.py:60-72)
-  const uint32_t m = (k0 == XLBN_BC_FULLWAY_BOUNCE_BACK ? 0x0000ffffu : 0u) | (k1 == XLBN_BC_FULLWAY_BOUNCE_BACK ? 0xffff0000u : 0u);
-  h2_collide_each<L>(h, omega, [&](auto l_, f32x2 out) {
-    constexpr int l = decltype(l_)::value;
-    const uint32_t o = tile_bits(__float22half2_rn(out.v));
-    if (!complex_bc) put(l_, (o & ~m) | (tile_bits(h[L::opp(l)]) & m));
-  });
-  if (!any_bc) return;
-  if (!complex_bc) {  // EquilibriumBC halves: bc_equilibrium.py:76-86 followed by the ordinary collision = a per-BC constant (bc_precompute_kernel)
-    if (k0 == XLBN_BC_EQUILIBRIUM) {
-      const float* e = p.table[id0].eq_out;
-      XLBN_FOR(Q, l)
-        Pack<TS, 1> a;
-        a.v[0] = __float2half_rn(e[l]);
-        gstore<TS, 1>(p.push[l] + cell, a);
-      XLBN_END
-    }
-    if (k1 == XLBN_BC_EQUILIBRIUM) {
-      const float* e = p.table[id1].eq_out;
-      XLBN_FOR(Q, l)
-        Pack<TS, 1> a;
-        a.v[0] = __float2half_rn(e[l]);
-        gstore<TS, 1>(p.push[l] + (cell + 1u), a);
-      XLBN_END
-    }
-    return;
+  const bool eq0 = k0 == XLBN_BC_EQUILIBRIUM, eq1 = k1 == XLBN_BC_EQUILIBRIUM;
+  const unsigned s0 = eq0 ? eq.slot_of[id0] : 0xffu, s1 = eq1 ? eq.slot_of[id1] : 0xffu;
+  const bool complex_bc = (id0 == 255) | (id1 == 255) | (k0 != XLBN_BC_NONE && k0 != XLBN_BC_FULLWAY_BOUNCE_BACK && !eq0) |
+                          (k1 != XLBN_BC_NONE && k1 != XLBN_BC_FULLWAY_BOUNCE_BACK && !eq1) | (eq0 && s0 == 0xffu) | (eq1 && s1 == 0xffu) |
+                          (eq0 && eq1 && s0 != s1);
+  // FullwayBounceBack halves: out[l] = f_post_stream[opp l], a bit copy (bc_fullway_bounce_back.py:60-72).
+  // EquilibriumBC halves: bc_equilibrium.py:76-86 followed by the ordinary collision = a per-BC constant, kept in shared memory.
+  const uint32_t m_fw = (k0 == XLBN_BC_FULLWAY_BOUNCE_BACK ? 0x0000ffffu : 0u) | (k1 == XLBN_BC_FULLWAY_BOUNCE_BACK ? 0xffff0000u : 0u);
+  const uint32_t m_eq = complex_bc ? 0u : ((eq0 ? 0x0000ffffu : 0u) | (eq1 ? 0xffff0000u : 0u));
+  if (!XLBN_ANY(0xffffffffu, m_eq != 0u)) {  // warp-uniform: walls only
+    h2_collide_each<L>(h, omega, [&](auto l_, f32x2 out) {
+      constexpr int l = decltype(l_)::value;
+      const uint32_t o = tile_bits(__float22half2_rn(out.v));
+      if (!complex_bc) put(l_, (o & ~m_fw) | (tile_bits(h[L::opp(l)]) & m_fw));
+    });
+  } else {
+    const uint32_t* ew = eq.word[eq0 ? s0 : (eq1 ? s1 : 0u)];  // lanes without an EquilibriumBC cell read slot 0 and mask it away
+    if (complex_bc) ew = eq.word[0];
+    h2_collide_each<L>(h, omega, [&](auto l_, f32x2 out) {
+      constexpr int l = decltype(l_)::value;
+      const uint32_t o = tile_bits(__float22half2_rn(out.v));
+      if (!complex_bc) put(l_, (o & ~(m_fw | m_eq)) | (tile_bits(h[L::opp(l)]) & m_fw) | (ew[l] & m_eq));
+    });
   }
+  if (!complex_bc) return;
   // every other kind, and cells with id 255 (not written: nse_stepper.py:356-358): the scalar boundary routine of the direct kernel
   const unsigned nz = (unsigned)p.nz, j = 2u * t;
   const int y = g.y0 + (int)(j / nz), z0 = (int)(j & (nz - 1u));
@@ -253,7 +276,8 @@ __global__ void __launch_bounds__(kTileThreads, CTAS) step_tile_kernel(const __g
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // one per input stage: the bulk copies of the stage have landed
   uint64_t* empty = full + C::kInStages;                // one per input stage: all 8 consumer warps have taken their words
-  unsigned char* in0 = smem + kTileBarBytes;
+  TileEqTable& eq = *reinterpret_cast<TileEqTable*>(smem + kTileBarBytes);
+  unsigned char* in0 = smem + C::kFixedBytes;
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < C::kInStages; ++s) {
@@ -262,10 +286,12 @@ __global__ void __launch_bounds__(kTileThreads, CTAS) step_tile_kernel(const __g
     }
     mbar_init_fence();
   }
+  if (tid == 32) tile_eq_table_fill<L>(p, eq);
   __syncthreads();
 
   if (warp == kTileConsumers / 32) {
     // ---- producer: runs ahead of the consumers by up to kInStages tiles ----
+    const int pl = lane < L::Q ? lane : 0, pcx = L::ck(0, pl), pcy = L::ck(1, pl);
     int k = 0;
     for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++k) {
       const int s = k % C::kInStages;
@@ -278,7 +304,7 @@ __global__ void __launch_bounds__(kTileThreads, CTAS) step_tile_kernel(const __g
       if (lane < L::Q) {
         const __half* src[2];
         unsigned dst[2], count[2];
-        const int n = tile_plan<L>(p, lane, g, rows, src, dst, count);
+        const int n = tile_plan<L>(p, lane, pcx, pcy, g, rows, src, dst, count);
         for (int i = 0; i < n; ++i) bulk_load(stage + lane * kTileRowBytes + dst[i] * 2u, src[i], count[i] * 2u, full + s);
       } else if (lane == L::Q) {
         bulk_load(stage + L::Q * kTileRowBytes, p.bc + g.cell0, kTileCells, full + s);
@@ -288,33 +314,39 @@ __global__ void __launch_bounds__(kTileThreads, CTAS) step_tile_kernel(const __g
   }
 
   // ---- consumers: 8 independent warps, no CTA-wide synchronisation ----
-  const unsigned t = (unsigned)tid;
   int k = 0;
   for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++k) {
     const int s = k % C::kInStages;
     const uint32_t phase = (uint32_t)(k / C::kInStages) & 1u;
     const TileGeom g = tile_geom(p, tile, rows, tiles_per_plane);
     const unsigned char* stage = in0 + s * C::kInBytes;
+    // which 32 words a warp takes rotates from tile to tile: in a closed box the floor / lid cells sit at the two ends of EVERY row, and
+    // the stage ring advances at the pace of the slowest warp — so every warp takes its turn with them
+    const unsigned t = ((unsigned)tid + 32u * (unsigned)(k & 7)) & (unsigned)(kTileConsumers - 1);
     __half2 h[L::Q];
     unsigned ids;
     mbar_wait(full + s, phase);
     tile_load<L>(p, reinterpret_cast<const uint32_t*>(stage), stage + L::Q * kTileRowBytes, t, h, ids);
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);  // the stage can be refilled while this tile is computed
-    tile_compute<L>(p, h, ids, t, g);
+    tile_compute<L>(p, eq, h, ids, t, g);
   }
 }
 
 template <class L, int CTAS>
 int launch_step_tile(const StepParams<__half>& p, int x_count, cudaStream_t stream) {
   using C = TileCfg<L, CTAS>;
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    XLBN_CUDA_OK(cudaGetDevice(&dev));
-    XLBN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  static int sm_counts[64] = {0};  // per device: the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
+  int dev = 0;
+  XLBN_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(XLBN_E_STATE, "tile kernel: device ordinal %d", dev);
+  if (sm_counts[dev] == 0) {
+    int n = 0;
+    XLBN_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     XLBN_CUDA_OK(cudaFuncSetAttribute(step_tile_kernel<L, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    sm_counts[dev] = n;
   }
+  const int sm_count = sm_counts[dev];
   const int rows = kTileCells / p.nz, tiles_per_plane = p.ny / rows;
   const long long n_tiles = (long long)tiles_per_plane * x_count;
   if (n_tiles > 0x7fffffffLL) return fail(XLBN_E_SHAPE, "tile kernel: %lld tiles", n_tiles);

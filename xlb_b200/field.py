@@ -29,6 +29,12 @@ class Field(torch.Tensor):
         return a.astype(dtype) if dtype is not None else a
 
 
+class WarpField(Field):
+    """A field created on the WARP convention (WarpGrid.create_field).  Same memory, same behaviour; the marker only exists so that a
+    reference script's ``isinstance(f, jnp.ndarray)`` is False for it — as it is for a ``wp.array`` — and its ``wp.to_jax(f)`` branch is
+    taken (examples/cfd/lid_driven_cavity_2d.py:74-78 drops the trailing singleton axis of 2-D Warp fields there)."""
+
+
 def as_field(x, dtype=None, device=None) -> Field:
     """Convert numpy / python / tensor input to a contiguous Field."""
     if isinstance(x, torch.Tensor):

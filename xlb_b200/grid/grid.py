@@ -28,7 +28,7 @@ import torch
 
 from xlb_b200.compute_backend import ComputeBackend
 from xlb_b200.default_config import DefaultConfig
-from xlb_b200.field import Field
+from xlb_b200.field import Field, WarpField
 from xlb_b200.precision_policy import Precision
 
 
@@ -83,7 +83,7 @@ class Grid:
             t = torch.zeros(shape, dtype=tdtype, device=self.device)
         else:
             t = torch.full(shape, fill_value, dtype=tdtype, device=self.device)
-        return Field.wrap(t)
+        return t.as_subclass(WarpField) if self.compute_backend == ComputeBackend.WARP else Field.wrap(t)
 
     # -- index helpers ------------------------------------------------------------------------
     def bounding_box_indices(self, remove_edges: bool = False):
