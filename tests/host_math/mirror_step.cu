@@ -201,6 +201,18 @@ int MIRROR_NAME(int lattice, int collision, int compute_dtype, int store_dtype, 
   c.ghost_hi = ghost_hi;
   c.out_lo = out_lo;
   c.out_hi = out_hi;
+  static double eq_in[4][kMaxQ];  // as xlbn_stepper_create
+  static uint8_t eq_ids[4];
+  memset(eq_in, 0, sizeof(eq_in));
+  memset(eq_ids, 0, sizeof(eq_ids));
+  for (int id = 1, n = 0; id < 255 && n < 4; ++id) {
+    if (table[id].kind != XLBN_BC_EQUILIBRIUM) continue;
+    if (compute_dtype == XLBN_F32) equilibrium_on_host<MIRROR_LAT, float>(table[id].rho, table[id].u, eq_in[n]);
+    else equilibrium_on_host<MIRROR_LAT, double>(table[id].rho, table[id].u, eq_in[n]);
+    eq_ids[n++] = (uint8_t)id;
+  }
+  c.eq_in = &eq_in[0][0];
+  c.eq_ids = eq_ids;
   for (int a = 0; a < 3; ++a) c.force[a] = force ? force[a] : 0.0;
   c.smagorinsky = smagorinsky;
   if (lattice == MIRROR_TAG && collision == (MIRROR_COLL)) return host_step_policy<MIRROR_LAT, (MIRROR_COLL)>(c);

@@ -12,6 +12,8 @@ struct xlbn_stepper {
   double eq_omega;       // omega the EquilibriumBC constants in the table were computed for (NaN = never)
   xlbn::BcEntry* table;  // device, 256 entries
   int device;
+  double eq_in[4][xlbn::kMaxQ];  // feq(rho, u) of the first 4 EquilibriumBC ids in the compute dtype (StepParams::eq_in)
+  uint8_t eq_ids[4];
   bool forced;           // ForcedCollision (xlbn_stepper_set_force)
   double force[3];
   double smagorinsky;
@@ -136,6 +138,20 @@ int xlbn_stepper_create(const xlbn_stepper_desc* desc, xlbn_stepper** out) {
     s->has_equilibrium_bc |= host[i].kind == XLBN_BC_EQUILIBRIUM;
   }
   s->eq_omega = nan("");
+  memset(s->eq_in, 0, sizeof(s->eq_in));
+  memset(s->eq_ids, 0, sizeof(s->eq_ids));
+  for (int id = 1, n = 0; id < 255 && n < 4; ++id) {
+    if (host[id].kind != XLBN_BC_EQUILIBRIUM) continue;
+    auto fill = [&](auto lat) {
+      using L = decltype(lat);
+      if (desc->compute_dtype == XLBN_F32) equilibrium_on_host<L, float>(host[id].rho, host[id].u, s->eq_in[n]);
+      else equilibrium_on_host<L, double>(host[id].rho, host[id].u, s->eq_in[n]);
+    };
+    if (desc->lattice == XLBN_D2Q9) fill(D2Q9{});
+    else if (desc->lattice == XLBN_D3Q19) fill(D3Q19{});
+    else fill(D3Q27{});
+    s->eq_ids[n++] = (uint8_t)id;
+  }
   s->forced = false;
   s->force[0] = s->force[1] = s->force[2] = 0.0;
   s->smagorinsky = 0.17;  // smagorinsky_les_bgk.py:24
@@ -225,6 +241,8 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
   c.out_lo = c.out_hi = nullptr;
   for (int a = 0; a < 3; ++a) c.force[a] = s->force[a];  // physical components; the cell algebra uses L::c(), not kernel axes
   c.smagorinsky = s->smagorinsky;
+  c.eq_in = &s->eq_in[0][0];
+  c.eq_ids = s->eq_ids;
   const bool slab_2d = s->lattice == XLBN_D2Q9 && (halo || dom->x_begin != 0 || dom->x_count != dom->nx);
   if (slab_2d) {  // x-slab / partial x range in 2-D: kernel extents (nx, 1, ny), physical x on the kernel's slab axis (D2Q9X)
     if (s->forced) return fail(XLBN_E_UNSUPPORTED, "xlbn_step: forced collision on a 2-D slab / partial x range is not built");

@@ -5,5 +5,4 @@
 namespace xlbn {
 XLBN_DEFINE_STEP_DISPATCH(D2Q9X, XLBN_BGK)
 XLBN_DEFINE_STEP_DISPATCH(D2Q9X, XLBN_KBC)
-XLBN_DEFINE_STEP_DISPATCH(D2Q9X, XLBN_KBC | kLeanKbc)
 }  // namespace xlbn

@@ -5,6 +5,5 @@
 namespace xlbn {
 XLBN_DEFINE_STEP_DISPATCH(D2Q9, XLBN_BGK | XLBN_COLLISION_FORCED)
 XLBN_DEFINE_STEP_DISPATCH(D2Q9, XLBN_KBC | XLBN_COLLISION_FORCED)
-XLBN_DEFINE_STEP_DISPATCH(D2Q9, XLBN_KBC | kLeanKbc)  // tuning variant: register-lean KBC (cells_per_thread = 301)
 XLBN_DEFINE_STEP_DISPATCH(D2Q9, XLBN_KBC | kExactKbc)  // parity form: the reference's roundings (cells_per_thread = 300)
 }  // namespace xlbn

@@ -7,6 +7,5 @@ XLBN_DEFINE_STEP_DISPATCH(D3Q27, XLBN_BGK | XLBN_COLLISION_FORCED)
 XLBN_DEFINE_STEP_DISPATCH(D3Q27, XLBN_KBC | XLBN_COLLISION_FORCED)
 XLBN_DEFINE_STEP_DISPATCH(D3Q27, XLBN_SMAGORINSKY_LES_BGK)
 XLBN_DEFINE_STEP_DISPATCH(D3Q27, XLBN_SMAGORINSKY_LES_BGK | XLBN_COLLISION_FORCED)
-XLBN_DEFINE_STEP_DISPATCH(D3Q27, XLBN_KBC | kLeanKbc)  // tuning variant: register-lean KBC (cells_per_thread = 301)
 XLBN_DEFINE_STEP_DISPATCH(D3Q27, XLBN_KBC | kExactKbc)  // parity form: the reference's roundings (cells_per_thread = 300)
 }  // namespace xlbn

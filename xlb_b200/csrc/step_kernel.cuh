@@ -72,7 +72,14 @@ struct StepParams {
   // extended collision models only (appended: the layout above is what the base kernels were validated with)
   double force[3];     // ForcedCollision / ExactDifference body force
   double smagorinsky;  // SmagorinskyLESBGK coefficient
+  // EquilibriumBC at the INPUT side: feq(rho_bc, u_bc) of up to kEqSlots boundary ids, evaluated once on the host in the compute dtype
+  // (same expression, same IEEE roundings as equilibrium<>()).  A thread that owns such a cell replaces the pulled populations by
+  // these constants and takes the ordinary straight-line path — bc_equilibrium.py:76-86 followed by the collision, without a second
+  // copy of the collision code executed by a whole warp for one lid lane.
+  double eq_in[4][kMaxQ];
+  uint8_t eq_ids[4];  // boundary id of each slot, 0 = unused
 };
+constexpr int kEqSlots = 4;
 
 // ---- explicit global-space memory instructions (SASS: LDG / STG; the compiler cannot prove the address space of
 //      pointers that arrive inside a parameter struct and would emit generic LD / ST) --------------------------------
@@ -320,7 +327,10 @@ struct StepTraits {
                                                (kBaseCollision<COLL> == XLBN_SMAGORINSKY_LES_BGK ? 8 * kW : 0) + 5;
   static constexpr int kMinBlocksRaw = 65536 / (kThreads * (kRegs > 255 ? 255 : kRegs));
   static constexpr int kMinBlocksAuto = kMinBlocksRaw < 1 ? 1 : (kMinBlocksRaw > 12 ? 12 : kMinBlocksRaw);
-  static constexpr int kMinBlocks = XLBN_MINB_OVERRIDE > 0 ? XLBN_MINB_OVERRIDE : kMinBlocksAuto;
+  // fp64 compute, D3Q19 BGK, one cell per thread: 8 CTAs/SM (64 registers) measured 3 % faster than the 7 the budget formula gives and
+  // than 9 (profiles/r1_sweep_fp16_fp64_occupancy.txt)
+  static constexpr bool kF64Q19 = sizeof(TC) == 8 && L::Q == 19 && V == 1 && MODE == 0 && COLL == XLBN_BGK;
+  static constexpr int kMinBlocks = XLBN_MINB_OVERRIDE > 0 ? XLBN_MINB_OVERRIDE : (kF64Q19 ? 8 : kMinBlocksAuto);
 };
 
 // Store V cells (fused compute -> store conversion).  The outgoing face populations of planes 0 / nx-1 ALSO go straight
@@ -462,6 +472,24 @@ XLBN_DEV void step_body(const StepParams<TS>& p, const int x, const int y, const
   XLBN_END
 
   const TC omega = (TC)p.omega;
+  if (any_bc) {  // EquilibriumBC cells whose feq is in the parameter block: f = feq(rho_bc, u_bc), then they are ordinary cells
+    bool rest = false;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int id = ids.v[v];
+      if (id == 0) continue;
+      int slot = -1;
+#pragma unroll
+      for (int i = 0; i < kEqSlots; ++i)
+        if (p.eq_ids[i] == id) slot = i;
+      if (slot < 0) {
+        rest = true;
+        continue;
+      }
+      XLBN_FOR(Q, l) f[v][l] = (TC)p.eq_in[slot][l]; XLBN_END
+    }
+    any_bc = rest;
+  }
   if (!any_bc) {
     // straight-line path: no boundary cell among this thread's V cells (ends here, so that its register allocation is
     // independent of the boundary code)
@@ -923,10 +951,35 @@ struct StepCall {
   cudaStream_t stream;
   double force[3];  // extended collision models only
   double smagorinsky;
+  const double* eq_in;    // host: [4][kMaxQ] feq of the EquilibriumBC slots in the compute dtype (NULL: none)
+  const uint8_t* eq_ids;  // host: [4]
 };
 
 template <class L, int COLL>
 int dispatch_step(const StepCall& c);
+
+// Host: feq(rho, u) of an EquilibriumBC in the compute dtype T, the expression of equilibrium<>() operation by operation (plain IEEE
+// arithmetic: the host objects are compiled with -ffp-contract=off), stored as doubles (exact).  StepParams::eq_in.
+template <class L, class T>
+inline void equilibrium_on_host(double rho_d, const double* u_d, double* out) {
+  const T rho = (T)rho_d;
+  T u[L::D];
+  for (int d = 0; d < L::D; ++d) u[d] = (T)u_d[d];
+  T uu = u[0] * u[0];
+  for (int d = 1; d < L::D; ++d) uu = uu + u[d] * u[d];
+  const T usqr = T(1.5) * uu;
+  static_for_host<L::Q>([&](auto l_) {
+    constexpr int l = decltype(l_)::value;
+    T cu = T(0);
+    for (int d = 0; d < L::D; ++d) {
+      if (L::c(d, l) == 1) cu += u[d];
+      else if (L::c(d, l) == -1) cu -= u[d];
+    }
+    cu *= T(3.0);
+    const T feq = rho * T(L::w(l)) * (T(1.0) + cu * (T(1.0) + T(0.5) * cu) - usqr);
+    out[l] = (double)feq;
+  });
+}
 
 // Host: fold everything that depends only on (population, x-plane class) into the kernel's pointer tables.
 template <class L, class TS>
@@ -975,6 +1028,10 @@ int fill_step_params(const StepCall& c, StepParams<TS>& p) {
   p.omega = c.omega;
   for (int a = 0; a < 3; ++a) p.force[a] = c.force[a];
   p.smagorinsky = c.smagorinsky;
+  if (c.eq_in) {
+    memcpy(p.eq_in, c.eq_in, sizeof(p.eq_in));
+    memcpy(p.eq_ids, c.eq_ids, sizeof(p.eq_ids));
+  }
   return 0;
 }
 
