@@ -14,7 +14,7 @@ KERNELS = [  # (title, object, mangled-name fragment)
     ("D3Q19 BGK FP32FP32, one cell per thread (the headline kernel)", "step_inst_d3q19_bgk.o", "step_kernelINS_7LatticeINS_9D3Q19BaseEEELi0EffLi1ELi0EEEv"),
     ("D3Q19 BGK FP32FP16, half2-state pair path (direct loads)", "step_inst_d3q19_bgk.o", "step_kernelINS_7LatticeINS_9D3Q19BaseEEELi0Ef6__halfLi2ELi2EEEv"),
     ("D3Q19 BGK FP32FP16, tile kernel (TMA-fed, persistent), 2 CTAs/SM", "step_inst_d3q19_bgk.o", "step_tile_kernelINS_7LatticeINS_9D3Q19BaseEEELi2EEEv"),
-    ("D3Q27 KBC FP32FP32, register-lean formulation (default)", "step_inst_ext_d3q27.o", "step_kernelINS_7LatticeINS_9D3Q27BaseEEELi9EffLi1ELi0EEEv"),
+    ("D3Q27 KBC FP32FP32, register-lean formulation (default)", "step_inst_kbc_lean.o", "step_kernelINS_7LatticeINS_9D3Q27BaseEEELi9EffLi1ELi0EEEv"),
 ]
 
 
@@ -49,17 +49,19 @@ def regs(obj, frag):
 
 
 def straight_path(lines):
-    """The longest run of instructions without a local-memory access, CALL or EXIT in its interior that contains LDG / LDS and STG: the
-    no-boundary path of the interior-plane variant."""
-    best, start = (0, 0), 0
-    for i, l in enumerate(lines + ["EXIT"]):
-        op = opcode(l) if i < len(lines) else "EXIT"
-        if op.startswith(("EXIT", "CALL", "RET", "BRA")) and "@" not in l.split("*/")[-1][:12]:
-            seg = lines[start:i]
-            if any("STG" in s for s in seg) and any(("LDG" in s or "LDS" in s) for s in seg) and len(seg) > best[1] - best[0]:
-                best = (start, i)
+    """The no-boundary path of the interior-plane variant: among the stretches between UNCONDITIONAL control transfers (EXIT / RET / BRA
+    without a predicate; predicated branches and the CALL of the division slow path stay inside) that hold a full set of population
+    loads and stores, the one with the fewest local-memory instructions, then the shortest."""
+    segs, start = [], 0
+    for i, l in enumerate(lines):
+        body = l.split("*/", 1)[-1].strip()
+        if re.match(r"(EXIT|RET|BRA)\b", body):
+            segs.append(lines[start : i + 1])
             start = i + 1
-    return lines[best[0] : best[1]]
+    good = [g for g in segs if sum("STG" in x for x in g) >= 9 and sum(("LDG" in x or "LDS" in x) for x in g) >= 9]
+    if not good:
+        return []
+    return min(good, key=lambda g: (sum(("STL" in x or "LDL" in x) for x in g), len(g)))
 
 
 for title, obj, frag in KERNELS:
