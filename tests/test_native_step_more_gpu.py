@@ -175,3 +175,15 @@ def test_tile_kernel_refuses_shapes_it_cannot_tile():
         native_run(g, cells_per_thread=402)
     with pytest.raises(Exception, match="FP32FP16 BGK"):
         native_run(load_golden("cavity_d3q19_bgk_fp32"), cells_per_thread=402)
+
+
+def test_cuda_graph_loop_with_the_tile_kernel():
+    """stepper.run on a tile-eligible FP32FP16 grid: the persistent tile kernel (and the per-omega constants' refresh) inside a captured graph."""
+    g = tile_case("D3Q19", (8, 16, 64), 0, 3, True)
+    stepper, f_0, f_1, bm, mm = native_case(g)
+    a, b = stepper.run(f_0, f_1, bm, mm, g["omega"], 11)
+    stepper2, g_0, g_1, bm2, mm2 = native_case(g, cells_per_thread=1)  # scalar path, step by step
+    for i in range(11):
+        g_0, g_1 = stepper2(g_0, g_1, bm2, mm2, g["omega"], i)
+        g_0, g_1 = g_1, g_0
+    assert torch.equal(a, g_0)

@@ -632,18 +632,26 @@ XLBN_DEV void h2_collide_each(const __half2 (&h)[L::Q], const float omega_f, Emi
   XLBN_FOR(L::D - 1, d) uu = uu + mul_then_add_(u[d + 1], u[d + 1]); XLBN_END
   const f32x2 usqr = mul_then_add_(f32x2(1.5f), uu);
   const f32x2 omega(omega_f);
-  // equilibrium + BGK relaxation per population (quadratic_equilibrium.py:35-60, bgk.py:30-34)
-  XLBN_FOR(Q, l)
+  // equilibrium + BGK relaxation per population (quadratic_equilibrium.py:35-60, bgk.py:30-34).  Opposite directions are relaxed
+  // together: 3 c_opp.u = -(3 c.u) exactly (IEEE addition and multiplication are sign-symmetric), so the pair shares its cu.
+  auto relax = [&](auto l_, const f32x2 cu) {
+    constexpr int l = decltype(l_)::value;
     const f32x2 f(__half22float2(h[l]));
-    f32x2 cu(0.0f);
-    XLBN_FOR(L::D, d)
-      if constexpr (L::c(d, l) == 1) cu += u[d];
-      else if constexpr (L::c(d, l) == -1) cu -= u[d];
-    XLBN_END
-    cu *= f32x2(3.0f);
     // 1 + 0.5 cu may contract: the product is exact
     const f32x2 feq = mul_then_add_(rho * f32x2(L::w(l)), f32x2(1.0f) + mul_then_add_(cu, f32x2(1.0f) + f32x2(0.5f) * cu) - usqr);
     emit(l_, f - mul_then_add_(omega, f - feq));
+  };
+  XLBN_FOR(Q, l)
+    if constexpr (L::opp(l) >= l) {
+      f32x2 cu(0.0f);
+      XLBN_FOR(L::D, d)
+        if constexpr (L::c(d, l) == 1) cu += u[d];
+        else if constexpr (L::c(d, l) == -1) cu -= u[d];
+      XLBN_END
+      cu *= f32x2(3.0f);
+      relax(l_, cu);
+      if constexpr (L::opp(l) != l) relax(IC<L::opp(l)>{}, -cu);
+    }
   XLBN_END
 }
 
