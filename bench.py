@@ -373,10 +373,13 @@ def run_secondary(args, barrier):
 
 
 def run_e2e(args, stepper, grid, fields, cells_total, world, barrier):
-    """End to end through the public operator API with HOST buffers: the job's populations and masks start in pinned host
-    memory, are copied to the device inside the timed region, stepped K_e times with `stepper(...)` (per step the host
-    also sends `omega` and reads back a monitoring probe: the mid-x plane of all populations), and the final populations
-    are copied back to pinned host memory.  MLUPS = cells * K_e / wall-clock-on-device of all of that."""
+    """End to end through the public operator API with HOST buffers: the job's populations and masks start in pinned host memory and its
+    final populations end there; MLUPS = cells * K_e / device-timed duration of ALL of that.
+
+    N = 1: `stepper.run_streamed` — upload, K_e steps and download pipelined as a wavefront over x-planes (chunks of 32 planes; the
+    stepper's own kernels on partial x ranges; bit-identical to K_e ordinary calls, tests/test_native_step_more_gpu.py).
+    N > 1 (slab grids): the serial form — upload, K_e calls of `stepper(...)` with a per-step omega upload and probe-plane read-back,
+    download."""
     import torch
 
     f_0, f_1, bc_mask, missing_mask = fields
@@ -394,21 +397,36 @@ def run_e2e(args, stepper, grid, fields, cells_total, world, barrier):
     h_f.copy_(f_0)
     h_bc.copy_(bc_mask)
     h_mm.copy_(missing_mask)
+    streamed = world == 1 and 2 * k + 2 <= nx and hasattr(stepper, "run_streamed")
     d_omega = torch.empty(1, dtype=torch.float64, device=f_0.device)
     stepper.reset_halo() if world > 1 else None
+    if streamed:  # one untimed pass: stream creation, first-use allocations
+        stepper.run_streamed(h_f, h_out, f_0, f_1, bc_mask, missing_mask, 1.0, 2, host_bc_mask=h_bc, host_missing_mask=h_mm)
     barrier()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
-    f_0.copy_(h_f, non_blocking=True)
-    f_1.copy_(f_0)
-    bc_mask.copy_(h_bc, non_blocking=True)
-    missing_mask.copy_(h_mm, non_blocking=True)
-    for i in range(k):
+    if streamed:
         d_omega.copy_(h_omega, non_blocking=True)
-        f_0, f_1 = stepper(f_0, f_1, bc_mask, missing_mask, 1.0, i)
-        f_0, f_1 = f_1, f_0
-        h_probe.copy_(f_0[:, nx // 2], non_blocking=True)
-    h_out.copy_(f_0, non_blocking=True)
+        stepper.run_streamed(h_f, h_out, f_0, f_1, bc_mask, missing_mask, 1.0, k, host_bc_mask=h_bc, host_missing_mask=h_mm)
+        mm_bytes = h_mm.numel() if stepper._needs_missing else 0
+        h2d = (h_f.numel() * h_f.element_size() + h_bc.numel() + mm_bytes + 8) / k
+        d2h = (h_out.numel() * h_out.element_size()) / k
+        what = ("stepper.run_streamed: pinned-host populations + bc_mask" + (" + missing_mask" if mm_bytes else " (no boundary condition of this stepper reads missing_mask: not uploaded)")
+                + " -> device in 32-plane chunks, K steps as a wavefront behind the upload, final populations -> pinned host behind the last step; all inside the timed region")
+    else:
+        f_0.copy_(h_f, non_blocking=True)
+        f_1.copy_(f_0)
+        bc_mask.copy_(h_bc, non_blocking=True)
+        missing_mask.copy_(h_mm, non_blocking=True)
+        for i in range(k):
+            d_omega.copy_(h_omega, non_blocking=True)
+            f_0, f_1 = stepper(f_0, f_1, bc_mask, missing_mask, 1.0, i)
+            f_0, f_1 = f_1, f_0
+            h_probe.copy_(f_0[:, nx // 2], non_blocking=True)
+        h_out.copy_(f_0, non_blocking=True)
+        h2d = (h_f.numel() * h_f.element_size() + h_bc.numel() + h_mm.numel()) / k + 8
+        d2h = (h_out.numel() * h_out.element_size()) / k + h_probe.numel() * h_probe.element_size()
+        what = "pinned-host populations+masks -> device, K steps via stepper(...), per-step probe plane D2H, final populations -> pinned host"
     stop.record()
     barrier()
     ms = start.elapsed_time(stop)
@@ -418,12 +436,10 @@ def run_e2e(args, stepper, grid, fields, cells_total, world, barrier):
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    h2d = (h_f.numel() * h_f.element_size() + h_bc.numel() + h_mm.numel()) / k + 8
-    d2h = (h_out.numel() * h_out.element_size()) / k + h_probe.numel() * h_probe.element_size()
     return {
         "value": round(cells_total * k / (ms * 1e-3) / 1e6, 1), "unit": "MLUPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-        "steps": k, "bytes_are": "per rank (each of the %d ranks moves this much per step)" % world,
-        "what": "pinned-host populations+masks -> device, K steps via stepper(...), per-step probe plane D2H, final populations -> pinned host",
+        "steps": k, "ms": round(ms, 2), "finite": bool(torch.isfinite(h_out[:, :: max(1, nx // 8)]).all()),
+        "bytes_are": "per rank (each of the %d ranks moves this much per step)" % world, "what": what,
     }  # fmt: skip
 
 

@@ -187,3 +187,43 @@ def test_cuda_graph_loop_with_the_tile_kernel():
         g_0, g_1 = stepper2(g_0, g_1, bm2, mm2, g["omega"], i)
         g_0, g_1 = g_1, g_0
     assert torch.equal(a, g_0)
+
+
+@pytest.mark.parametrize("name,shape,steps,chunk", [("cavity", (48, 12, 16), 5, 8), ("cavity", (40, 8, 64), 9, 7), ("sphere", (64, 16, 16), 6, 16)])
+def test_streamed_host_job_is_bit_identical_to_the_ordinary_loop(name, shape, steps, chunk):
+    """stepper.run_streamed: upload, n steps and download overlapped as a wavefront over x-planes (in-place buffer reuse, the planes next to
+    the periodic wrap finished in a tail) must give the bits of n ordinary calls — closed box with lid (FP32FP16: tile kernel on partial x
+    ranges for the second case) and a tunnel with Regularized inlet / outflow / Halfway body (aux values in f_1[0], missing bits)."""
+    from oracle import lbm_numpy as O
+
+    if name == "cavity":
+        g = tile_case("D3Q19", shape, steps, 5, True)
+        if shape[2] != 64:
+            g["policy"] = "FP32FP32"
+            g["f_init"] = g["f_init"].astype(np.float32)
+    else:
+        g0 = load_golden("warp_sphere_d3q19_bgk_fp32fp16")
+        lat = O.Lattice("D3Q19")
+        box, bne = O.bounding_box_indices(shape), O.bounding_box_indices(shape, remove_edges=True)
+        walls = np.unique(np.concatenate([box[k] for k in ("bottom", "top", "front", "back")], axis=1), axis=-1)
+        X, Y, Z = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+        body = np.array(np.where((X - 20) ** 2 + (Y - 8) ** 2 + (Z - 8) ** 2 < 10))
+        pv = np.zeros((3, shape[1], shape[2]), np.float32)
+        pv[0] = 0.03
+        g = dict(g0)
+        g.update(shape=shape, steps=steps, policy="FP32FP32", f_init=O.initialize_eq(shape, lat, "FP32FP32"))
+        g["bcs"] = [dict(kind="fullway", id=1, indices=walls), dict(kind="regularized", id=2, indices=bne["left"], bc_type="velocity", prescribed=pv),
+                    dict(kind="outflow", id=3, indices=bne["right"]), dict(kind="halfway", id=4, indices=body)]  # fmt: skip
+    want, _, _ = native_run(g)
+    stepper, f_0, f_1, bm, mm = native_case(g)
+    host_f = f_0.cpu().pin_memory()
+    host_out = torch.empty_like(host_f).pin_memory()
+    h_bm, h_mm = bm.cpu().pin_memory(), mm.cpu().pin_memory()
+    aux = f_1.clone()  # f_1 carries the prescribed values of Zou-He / Regularized cells (boundary_condition.py:151): part of the job's device state
+    bm.zero_()
+    f_0.zero_()
+    f_1.copy_(aux)
+    final = stepper.run_streamed(host_f, host_out, f_0, f_1, bm, mm, g["omega"], steps, host_bc_mask=h_bm, host_missing_mask=h_mm, chunk_planes=chunk)
+    torch.cuda.synchronize()
+    assert np.array_equal(host_out.numpy(), want), f"{int((host_out.numpy() != want).sum())} values differ"
+    assert np.array_equal(final.numpy(), want)

@@ -72,6 +72,7 @@ struct TileCfg {
   static constexpr int kSmemBytes = kFixedBytes + kInStages * kInBytes;
   static_assert(L::Q + 1 <= 32, "one producer lane per population + one for the ids");
   static_assert(kInStages >= 2, "at least double buffering");
+  static_assert(2 * kInStages * 8 <= 64 && kInStages * sizeof(unsigned) * 3 <= 64, "barriers and tile geometries share the first 128 bytes");
 };
 
 struct TileGeom {
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(kTileThreads, CTAS) step_tile_kernel(const __g
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // one per input stage: the bulk copies of the stage have landed
   uint64_t* empty = full + C::kInStages;                // one per input stage: all 8 consumer warps have taken their words
+  TileGeom* geoms = reinterpret_cast<TileGeom*>(smem + 64);  // per input stage: where the tile in it lives (written by the producer)
   TileEqTable& eq = *reinterpret_cast<TileEqTable*>(smem + kTileBarBytes);
   unsigned char* in0 = smem + C::kFixedBytes;
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -299,7 +301,10 @@ __global__ void __launch_bounds__(kTileThreads, CTAS) step_tile_kernel(const __g
       mbar_wait(empty + s, phase ^ 1u);  // first round: passes at once
       const TileGeom g = tile_geom(p, tile, rows, tiles_per_plane);
       unsigned char* stage = in0 + s * C::kInBytes;
-      if (lane == 0) mbar_expect_tx(full + s, (uint32_t)C::kInBytes);
+      if (lane == 0) {
+        geoms[s] = g;  // the consumers read it after the stage's barrier: the 2 integer divisions of tile_geom are done once per tile
+        mbar_expect_tx(full + s, (uint32_t)C::kInBytes);
+      }
       __syncwarp();
       if (lane < L::Q) {
         const __half* src[2];
@@ -318,7 +323,6 @@ __global__ void __launch_bounds__(kTileThreads, CTAS) step_tile_kernel(const __g
   for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++k) {
     const int s = k % C::kInStages;
     const uint32_t phase = (uint32_t)(k / C::kInStages) & 1u;
-    const TileGeom g = tile_geom(p, tile, rows, tiles_per_plane);
     const unsigned char* stage = in0 + s * C::kInBytes;
     // which 32 words a warp takes rotates from tile to tile: in a closed box the floor / lid cells sit at the two ends of EVERY row, and
     // the stage ring advances at the pace of the slowest warp — so every warp takes its turn with them
@@ -326,6 +330,7 @@ __global__ void __launch_bounds__(kTileThreads, CTAS) step_tile_kernel(const __g
     __half2 h[L::Q];
     unsigned ids;
     mbar_wait(full + s, phase);
+    const TileGeom g = geoms[s];
     tile_load<L>(p, reinterpret_cast<const uint32_t*>(stage), stage + L::Q * kTileRowBytes, t, h, ids);
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);  // the stage can be refilled while this tile is computed

@@ -261,6 +261,108 @@ class IncompressibleNavierStokesStepper(Stepper):
             return f_1, f_0
         return f_0, f_1
 
+    def run_streamed(self, host_f, host_out, f_0, f_1, bc_mask, missing_mask, omega, n_steps, host_bc_mask=None, host_missing_mask=None, chunk_planes=32):
+        """A whole HOST-RESIDENT job — upload, ``n_steps`` time steps, download — as one pipeline over x-planes.
+
+        ``host_f`` (pinned, [q, nx, ny, nz], store dtype) holds the populations at step 0, ``host_out`` (pinned, same shape) receives
+        them at step ``n_steps``; ``f_0`` / ``f_1`` / ``bc_mask`` / ``missing_mask`` are the device fields of ``prepare_fields`` (the masks
+        are uploaded from ``host_bc_mask`` / ``host_missing_mask`` first when those are given; the bool mask only if a boundary condition of
+        this stepper reads it).  Returns the device field that holds the final populations.
+
+        Not part of the reference API (its loop, mlups_3d.py:77-80, never touches the host).  For a short run of a large grid the PCIe
+        transfers dominate — 20 steps of 512^3 are 65 ms of kernels between two 190 ms copies — so the three phases are overlapped: the
+        populations arrive in chunks of ``chunk_planes`` x-planes; step s works on the planes whose x-neighbours step s-1 has finished
+        (a wavefront that trails the upload by one plane per step: ``[s, (c+1) C - s)`` after chunk c), the two buffers are reused in
+        place (step s overwrites plane p of step s-2's array only after step s-1 has read it, which stream order guarantees), the planes
+        next to the periodic wrap (``[0, s)`` and ``[nx - s, nx)`` for step s) are finished in a short tail once everything is on the
+        device, and the download of the final planes runs on a third stream behind the last step's wavefront.  Same kernels, same
+        arithmetic: the result is bit-identical to ``n_steps`` ordinary calls (tests/test_native_step_more_gpu.py).
+        Single-device 3-D grids; ``omega`` is constant over the run."""
+        if self.grid is not None and self.grid.nDevices > 1:
+            raise NotImplementedError("run_streamed(): single-device grids only")
+        vs = self.velocity_set
+        if vs.d != 3:
+            raise NotImplementedError("run_streamed(): 3-D grids only")
+        n_steps, C_ = int(n_steps), max(1, int(chunk_planes))
+        for name, t in (("f_0", f_0), ("f_1", f_1), ("bc_mask", bc_mask)):
+            native.require_cuda(t, name)
+        if tuple(host_f.shape) != tuple(f_0.shape) or tuple(host_out.shape) != tuple(f_0.shape) or host_f.dtype != f_0.dtype or host_out.dtype != f_0.dtype:
+            raise ValueError("host_f / host_out must match the device populations in shape and dtype")
+        nx, ny, nz = native.dims_of(f_0, vs.d)
+        if 2 * n_steps + 2 > nx:
+            raise ValueError(f"run_streamed(): {n_steps} steps need nx >= {2 * n_steps + 2} planes (nx = {nx}); use the ordinary loop")
+        handle = self._native_handle(f_0.device)
+        main = torch.cuda.current_stream(f_0.device)
+        if not hasattr(self, "_streams"):
+            self._streams = (torch.cuda.Stream(device=f_0.device), torch.cuda.Stream(device=f_0.device))
+        up, down = self._streams
+        up.wait_stream(main)
+        down.wait_stream(main)
+        L = native.lib()
+        q = vs.q
+        with torch.cuda.stream(up):
+            if host_bc_mask is not None:
+                bc_mask.copy_(host_bc_mask, non_blocking=True)
+            if host_missing_mask is not None and self._needs_missing:
+                missing_mask.copy_(host_missing_mask, non_blocking=True)
+            masks_ready = torch.cuda.Event()
+            masks_ready.record(up)
+            n_chunks = (nx + C_ - 1) // C_
+            arrived = []
+            for c in range(n_chunks):
+                a, b = c * C_, min(nx, (c + 1) * C_)
+                for l in range(q):  # one contiguous run per population
+                    f_0[l, a:b].copy_(host_f[l, a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(up)
+                arrived.append(ev)
+        main.wait_event(masks_ready)
+        bits = self._missing_bits(missing_mask) if self._needs_missing else None
+        native.check(L.xlbn_stepper_prepare(handle, float(omega), native.stream_of(f_0)))
+        bufs = (f_0, f_1)
+        st = native.stream_of(f_0)
+
+        def launch(s, a, b):  # step s (1-based) on planes [a, b): reads bufs[(s - 1) % 2], writes bufs[s % 2]
+            if b <= a:
+                return
+            dom = native.Domain(nx, ny, nz, int(a), int(b - a))
+            src, dst = bufs[(s - 1) % 2], bufs[s % 2]
+            native.check(L.xlbn_step(handle, native.ptr(src), native.ptr(dst), native.ptr(bc_mask), native.ptr(bits), C.byref(dom), float(omega), s - 1, None, st))
+
+        final = bufs[n_steps % 2]
+
+        def download(a, b, after):
+            if b <= a:
+                return
+            down.wait_event(after)
+            with torch.cuda.stream(down):
+                for l in range(q):
+                    host_out[l, a:b].copy_(final[l, a:b], non_blocking=True)
+
+        done_to = n_steps  # planes [n_steps, done_to) of the final step are finished
+        for c in range(n_chunks):
+            main.wait_event(arrived[c])
+            top = min(nx, (c + 1) * C_)
+            for s in range(1, n_steps + 1):
+                lo = max(s, c * C_ - s) if c else s
+                launch(s, lo, min(nx - s, top - s))
+            new_to = max(done_to, min(nx - n_steps, top - n_steps))
+            if new_to > done_to:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                download(done_to, new_to, ev)
+                done_to = new_to
+        for s in range(1, n_steps + 1):  # the planes next to the periodic wrap, once everything is on the device
+            launch(s, 0, s)
+            launch(s, nx - s, nx)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        download(0, n_steps, ev)
+        download(done_to, nx, ev)
+        main.wait_stream(down)
+        main.wait_stream(up)
+        return final
+
     def reset_halo(self):
         """Re-prime the ghost planes from the populations passed to the next call (use after modifying the populations
         outside the stepper on a slab grid).  Collective: synchronises the device and all ranks, then skips two halo
