@@ -101,8 +101,10 @@ typedef struct xlbn_stepper_desc {
                                      This is what 0 selects for an unforced KBC stepper.
                                300 = KBC only: the literal three-array formulation with the reference's own roundings (IEEE divisions,
                                      nothing fused): bit-identical to the reference kernel; the parity form, ~2x slower
-                               402 / 403 = FP32FP16 BGK only: the persistent TMA-fed tile kernel with 2 / 3 CTAs per SM (csrc/step_tile.cuh);
-                                     needs nz | 512, nz % 8 == 0, ny % (512 / nz) == 0, no halo handle on the call */
+                               402 = FP32FP16 BGK only: the persistent TMA-fed tile kernel (csrc/step_tile.cuh), what 0 selects where the
+                                     slab can be tiled: 1024-cell tiles if they fit the plane, else 512-cell tiles;
+                                     404 = 512-cell tiles; 403 = 512-cell tiles at three CTAs per SM (tuning variant).
+                                     Needs nz | 512, nz % 8 == 0, ny % (512 / nz) == 0, no halo handle on the call */
   const xlbn_bc_desc* bcs;  /* n_bc entries, copied */
 } xlbn_stepper_desc;
 

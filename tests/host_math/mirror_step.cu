@@ -81,11 +81,12 @@ int host_step_pair(const StepCall& c) {
 // The tile kernel (csrc/step_tile.cuh; cells_per_thread 402) with its asynchronous machinery replaced by what it amounts to: the
 // producer's copy plan executed with memcpy into an input stage, the 256 consumer threads of the tile run one after the other
 // (tile_load + tile_compute: the shipped per-thread code, which stores to the destination itself).
-template <class L>
+template <class L, int CELLS>
 int host_step_tile(const StepCall& c) {
+  constexpr int kTileCells = CELLS, kTileConsumers = TileDims<CELLS>::kConsumers, kTileRowBytes = TileDims<CELLS>::kRowBytes;
   StepParams<__half> p;
   if (int e = fill_step_params<L, __half>(c, p)) return e;
-  if (!tile_eligible<L>(p, c.f0, c.f1, c.ghost_lo, c.ghost_hi, c.out_lo != nullptr || c.out_hi != nullptr)) return fail(XLBN_E_SHAPE, "mirror: shape not eligible for the tile kernel");
+  if (!tile_eligible<L, CELLS>(p, c.f0, c.f1, c.ghost_lo, c.ghost_hi, c.out_lo != nullptr || c.out_hi != nullptr)) return fail(XLBN_E_SHAPE, "mirror: shape not eligible for the tile kernel");
   BcEntry* table = c.table_rw;  // bc_precompute_kernel
   for (int id = 0; id < 256; ++id) {
     if (table[id].kind != XLBN_BC_EQUILIBRIUM) continue;
@@ -95,7 +96,7 @@ int host_step_tile(const StepCall& c) {
     collide_cell<L, XLBN_BGK, float, false>(f, (float)c.omega);
     XLBN_FOR(L::Q, l) table[id].eq_out[l] = f[l]; XLBN_END
   }
-  using C = TileCfg<L, 2>;
+  using C = TileCfg<L, CELLS, 1>;
   const int rows = kTileCells / p.nz, tiles_per_plane = p.ny / rows, n_tiles = tiles_per_plane * c.x_count;
   static unsigned char in[C::kInBytes];
   static TileEqTable eq;
@@ -119,8 +120,8 @@ int host_step_tile(const StepCall& c) {
     for (unsigned t = 0; t < (unsigned)kTileConsumers; ++t) {  // the consumer threads
       __half2 h[L::Q];
       unsigned ids;
-      tile_load<L>(p, reinterpret_cast<const uint32_t*>(in), in + L::Q * kTileRowBytes, t, h, ids);
-      tile_compute<L>(p, eq, h, ids, t, g);
+      tile_load<L, CELLS>(p, reinterpret_cast<const uint32_t*>(in), in + L::Q * kTileRowBytes, t, h, ids);
+      tile_compute<L, CELLS>(p, eq, h, ids, t, g);
     }
   }
   return 0;
@@ -129,7 +130,9 @@ int host_step_tile(const StepCall& c) {
 template <class L, int COLL, class TC, class TS>
 int host_step_v(const StepCall& c) {
   if constexpr (COLL == XLBN_BGK && sizeof(TC) == 4 && sizeof(TS) == 2 && L::D == 3)
-    if (c.requested_v == 402) return host_step_tile<L>(c);
+    if (c.requested_v == 404) return host_step_tile<L, 512>(c);
+  if constexpr (COLL == XLBN_BGK && sizeof(TC) == 4 && sizeof(TS) == 2 && L::D == 3)
+    if (c.requested_v == 402) return host_step_tile<L, 1024>(c);  // 1024-cell tiles (the library falls back to 512 when they do not fit)
   if (c.requested_v == 1) return host_step<L, COLL, TC, TS, 1>(c);
   if constexpr (!kExtCollision<COLL> && sizeof(TC) == 4) {
     if (c.requested_v == 102) return host_step_pair<L, COLL, TS, 1>(c);

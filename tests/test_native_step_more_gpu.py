@@ -28,7 +28,7 @@ def is_exact_case(g, v):
         return False
     if g["collision"] == "KBC":
         return v == 300  # the literal formulation with the reference's roundings (kExactKbc); the lean default is tolerance-only
-    return g["collision"] == "BGK" and v in (0, 1, 2, 4, 8, 202, 203, 402, 403)
+    return g["collision"] == "BGK" and v in (0, 1, 2, 4, 8, 202, 203, 402, 403, 404)
 
 
 def check_step_case(name, backend, v=0):
@@ -129,7 +129,7 @@ def test_omega_may_change_every_step_without_a_host_sync():
 
 
 TILE_SHAPES = [("D3Q19", (3, 4, 512), True), ("D3Q19", (4, 8, 128), True), ("D3Q27", (3, 16, 64), True), ("D3Q19", (2, 64, 8), False), ("D3Q27", (5, 2, 256), False),
-               ("D3Q19", (1, 32, 16), True), ("D3Q19", (40, 64, 64), True), ("D3Q27", (33, 32, 128), True)]  # fmt: skip
+               ("D3Q19", (1, 32, 16), True), ("D3Q19", (40, 64, 64), True), ("D3Q27", (33, 32, 128), True), ("D3Q19", (2, 128, 8), False), ("D3Q27", (3, 6, 512), True)]  # fmt: skip
 
 
 @pytest.mark.parametrize("lattice,shape,walls", TILE_SHAPES)
@@ -139,10 +139,9 @@ def test_tile_kernel_is_bit_identical_to_the_reference_kernel(lattice, shape, wa
     the direct half2-state kernel."""
     g = tile_case(lattice, shape, 12, 11, walls)
     ref, _, _ = c_oracle_run(g)
-    f, _, _ = native_run(g, cells_per_thread=402)
-    assert np.array_equal(f, ref), f"{int((f != ref).sum())} of {f.size} values differ from the reference kernel's, rel err {rel_err(f, ref):.3e}"
-    f2, _, _ = native_run(g, cells_per_thread=202)
-    assert np.array_equal(f, f2)
+    for v in (402, 404, 202):  # tile kernel (1024-cell tiles where they fit the plane, else 512), 512-cell tiles, direct-load pair path
+        f, _, _ = native_run(g, cells_per_thread=v)
+        assert np.array_equal(f, ref), f"cells_per_thread={v}: {int((f != ref).sum())} of {f.size} values differ from the reference kernel's, rel err {rel_err(f, ref):.3e}"
 
 
 def test_tile_kernel_with_every_boundary_kind_and_solid_cells():
@@ -164,7 +163,7 @@ def test_tile_kernel_with_every_boundary_kind_and_solid_cells():
                 dict(kind="outflow", id=3, indices=bne["right"]), dict(kind="halfway", id=4, indices=body)]  # fmt: skip
     g["solid255"] = np.array([[12], [16], [32]])
     ref, _, _ = c_oracle_run(g)
-    for v in (402, 202, 1):
+    for v in (402, 404, 202, 1):
         f, _, _ = native_run(g, cells_per_thread=v)
         assert np.array_equal(f, ref), f"cells_per_thread={v}: {int((f != ref).sum())} of {f.size} values differ, rel err {rel_err(f, ref):.3e}"
 

@@ -874,25 +874,30 @@ int launch_step_base(const StepParams<TS>& p, int x_count, int requested_v, cons
   constexpr bool can_h2 = sizeof(TC) == 4 && sizeof(TS) == 2 && COLL == XLBN_BGK;
   if (req == 0) req = can_h2 ? 202 : 1;
 #if !XLBN_ON_HOST
-  if constexpr (can_h2 && L::D == 3) {  // FP32FP16 BGK default: the tile kernel wherever the slab can be tiled (B200: 0.82 vs 0.69 of the roofline)
-    if (requested_v == 0 && tile_eligible<L>(p, f0, f1, g0, g1, o0 != nullptr || o1 != nullptr)) req = 402;
-  }
-  if (req == 402 || req == 403) {  // the tile kernel (step_tile.cuh), explicitly: 402 = two CTAs per SM, 403 = three (D3Q19)
-    if constexpr (can_h2 && L::D == 3) {
-      if (!tile_eligible<L>(p, f0, f1, g0, g1, o0 != nullptr || o1 != nullptr))
-        return fail(XLBN_E_SHAPE, "cells_per_thread = 402 / 403: the tile kernel needs nz | 512, nz %% 8 == 0, ny %% (512 / nz) == 0, 16-byte aligned arrays and no halo handle (nz = %d, ny = %d)", p.nz, p.ny);
+  // FP32FP16 BGK on 3-D lattices: the tile kernel (step_tile.cuh) wherever the slab can be tiled — 1024-cell tiles (16 consumer warps, one
+  // CTA per SM) if they fit the plane, else 512-cell tiles (8 consumer warps, two CTAs per SM).  B200, 512^3 cavity: 0.93 / 0.87 of the
+  // roofline against 0.70 for the direct-load pair path.  402 = that choice, explicitly; 404 = 512-cell tiles; 403 = 512-cell tiles, three
+  // CTAs per SM (D3Q19; a tuning variant that spills).
+  if constexpr (can_h2 && L::D == 3) {
+    const bool peers = o0 != nullptr || o1 != nullptr;
+    const bool fits1024 = tile_eligible<L, 1024>(p, f0, f1, g0, g1, peers), fits512 = tile_eligible<L, 512>(p, f0, f1, g0, g1, peers);
+    if (requested_v == 0 && (fits1024 || fits512)) req = 402;
+    if (req == 402 || req == 403 || req == 404) {
+      if (!(req == 402 ? (fits1024 || fits512) : fits512))
+        return fail(XLBN_E_SHAPE, "cells_per_thread = %d: the tile kernel needs nz | 512, nz %% 8 == 0, ny %% (512 / nz) == 0, 16-byte aligned arrays and no halo handle (nz = %d, ny = %d)", req, p.nz, p.ny);
       if (eq_omega_state && !(p.omega == *eq_omega_state)) {
         bc_precompute_kernel<L, COLL><<<1, 256, 0, stream>>>(table_rw, (float)p.omega);
         XLBN_LAUNCH_OK("bc_precompute_kernel");
         *eq_omega_state = p.omega;
       }
       if constexpr (L::Q <= 19) {
-        if (req == 403) return launch_step_tile<L, 3>(p, x_count, stream);
+        if (req == 403) return launch_step_tile<L, 512, 3>(p, x_count, stream);
       }
-      return launch_step_tile<L, 2>(p, x_count, stream);
-    } else {
-      return fail(XLBN_E_ARG, "cells_per_thread = 402 / 403: the tile kernel exists for FP32FP16 BGK on 3-D lattices only");
+      if (req == 402 && fits1024) return launch_step_tile<L, 1024, 1>(p, x_count, stream);
+      return launch_step_tile<L, 512, 2>(p, x_count, stream);
     }
+  } else {
+    if (req == 402 || req == 403 || req == 404) return fail(XLBN_E_ARG, "cells_per_thread = %d: the tile kernel exists for FP32FP16 BGK on 3-D lattices only", req);
   }
 #endif
   if (req == 202 || req == 203) {

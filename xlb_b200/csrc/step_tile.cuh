@@ -29,10 +29,16 @@
 
 namespace xlbn {
 
-constexpr int kTileCells = 512;
-constexpr int kTileConsumers = 256;               // consumer threads = half2 words per population row of a tile
-constexpr int kTileThreads = kTileConsumers + 32;  // + the producer warp
-constexpr int kTileRowBytes = kTileCells * 2;
+// CELLS = cells per tile (512: 8 consumer warps, two CTAs per SM; 1024: 16 consumer warps, one CTA per SM, 2 KB bulk copies where a
+// population row is 1 KB — measured 0.93 against 0.87 of the roofline for the 512^3 cavity: half as many bulk copies per byte and one
+// stage ring shared by twice as many warps).  The kernel takes it as a template argument; xlbn_step picks the largest that tiles the slab.
+template <int CELLS>
+struct TileDims {
+  static constexpr int kCells = CELLS;
+  static constexpr int kConsumers = CELLS / 2;       // consumer threads = half2 words per population row of a tile
+  static constexpr int kThreads = kConsumers + 32;   // + the producer warp
+  static constexpr int kRowBytes = CELLS * 2;
+};
 constexpr int kTileBarBytes = 128;
 XLBN_DEV uint32_t tile_bits(__half2 h);
 constexpr int kTileEqSlots = 4;  // EquilibriumBC ids whose constant update is kept in shared memory (more: those cells take the scalar routine)
@@ -63,9 +69,9 @@ XLBN_DEV void tile_eq_table_fill(const StepParams<__half>& p, TileEqTable& tab) 
 
 // CTAS = resident CTAs per SM the kernel is compiled for (register budget 65536 / (288 * CTAS)); input stages fill what is left of
 // the 227 KB of shared memory.
-template <class L, int CTAS>
+template <class L, int CELLS, int CTAS>
 struct TileCfg {
-  static constexpr int kInBytes = L::Q * kTileRowBytes + kTileCells;  // q population rows + 512 bc ids
+  static constexpr int kInBytes = L::Q * TileDims<CELLS>::kRowBytes + CELLS;  // q population rows + the tile's bc ids
   static constexpr int kFixedBytes = kTileBarBytes + (int)((sizeof(TileEqTable) + 127) / 128 * 128);
   static constexpr int kMaxStages = (227 * 1024 / CTAS - 1024 - kFixedBytes) / kInBytes;
   static constexpr int kInStages = kMaxStages > 4 ? 4 : kMaxStages;
@@ -150,8 +156,9 @@ XLBN_DEV uint32_t tile_bits(__half2 h) {
 }
 
 // Thread t of a tile: its two cells' post-stream populations (as half2 words) and bc ids out of an input stage.
-template <class L>
+template <class L, int CELLS>
 XLBN_DEV void tile_load(const StepParams<__half>& p, const uint32_t* in_words, const uint8_t* in_ids, const unsigned t, __half2 (&h)[L::Q], unsigned& ids) {
+  constexpr int kTileConsumers = TileDims<CELLS>::kConsumers;
   const unsigned nz = (unsigned)p.nz, z0 = (2u * t) & (nz - 1u);  // nz is a power of two (a divisor of 512)
   const unsigned tp = (z0 == 0u) ? t + nz / 2u - 1u : t - 1u;          // word holding element z0 - 1 of the same row (periodic in z)
   const unsigned tn = (z0 + 2u == nz) ? t + 1u - nz / 2u : t + 1u;     // word holding element z0 + 2
@@ -175,7 +182,7 @@ XLBN_DEV void tile_load(const StepParams<__half>& p, const uint32_t* in_words, c
 }
 
 // Collide the two cells and store; boundary cells as described at the top of the file.
-template <class L>
+template <class L, int CELLS>
 XLBN_DEV void tile_compute(const StepParams<__half>& p, const TileEqTable& eq, const __half2 (&h)[L::Q], const unsigned ids, const unsigned t, const TileGeom& g) {
   using TS = __half;
   constexpr int Q = L::Q;
@@ -239,8 +246,9 @@ XLBN_DEV void tile_compute(const StepParams<__half>& p, const TileEqTable& eq, c
   else store_cells<L, float, TS, 2, 0, false>(p, cell, pk, fs);
 }
 
-template <class L>
+template <class L, int CELLS>
 bool tile_eligible(const StepParams<__half>& p, const void* f0, const void* f1, const void* ghost_lo, const void* ghost_hi, bool has_peers) {
+  constexpr int kTileCells = CELLS;
   auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % 16) == 0; };
   if (has_peers || p.nz < 8 || p.nz > kTileCells || (kTileCells % p.nz) != 0 || (p.nz % 8) != 0) return false;
   const int rows = kTileCells / p.nz;
@@ -270,10 +278,11 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint3
 }
 }  // namespace tile_ptx
 
-template <class L, int CTAS>
-__global__ void __launch_bounds__(kTileThreads, CTAS) step_tile_kernel(const __grid_constant__ StepParams<__half> p, const int n_tiles, const int rows, const int tiles_per_plane) {
+template <class L, int CELLS, int CTAS>
+__global__ void __launch_bounds__(TileDims<CELLS>::kThreads, CTAS) step_tile_kernel(const __grid_constant__ StepParams<__half> p, const int n_tiles, const int rows, const int tiles_per_plane) {
   using namespace tile_ptx;
-  using C = TileCfg<L, CTAS>;
+  using C = TileCfg<L, CELLS, CTAS>;
+  constexpr int kTileCells = CELLS, kTileConsumers = TileDims<CELLS>::kConsumers, kTileRowBytes = TileDims<CELLS>::kRowBytes;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // one per input stage: the bulk copies of the stage have landed
   uint64_t* empty = full + C::kInStages;                // one per input stage: all 8 consumer warps have taken their words
@@ -326,21 +335,22 @@ __global__ void __launch_bounds__(kTileThreads, CTAS) step_tile_kernel(const __g
     const unsigned char* stage = in0 + s * C::kInBytes;
     // which 32 words a warp takes rotates from tile to tile: in a closed box the floor / lid cells sit at the two ends of EVERY row, and
     // the stage ring advances at the pace of the slowest warp — so every warp takes its turn with them
-    const unsigned t = ((unsigned)tid + 32u * (unsigned)(k & 7)) & (unsigned)(kTileConsumers - 1);
+    const unsigned t = ((unsigned)tid + 32u * (unsigned)(k & (kTileConsumers / 32 - 1))) & (unsigned)(kTileConsumers - 1);
     __half2 h[L::Q];
     unsigned ids;
     mbar_wait(full + s, phase);
     const TileGeom g = geoms[s];
-    tile_load<L>(p, reinterpret_cast<const uint32_t*>(stage), stage + L::Q * kTileRowBytes, t, h, ids);
+    tile_load<L, CELLS>(p, reinterpret_cast<const uint32_t*>(stage), stage + L::Q * kTileRowBytes, t, h, ids);
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);  // the stage can be refilled while this tile is computed
-    tile_compute<L>(p, eq, h, ids, t, g);
+    tile_compute<L, CELLS>(p, eq, h, ids, t, g);
   }
 }
 
-template <class L, int CTAS>
+template <class L, int CELLS, int CTAS>
 int launch_step_tile(const StepParams<__half>& p, int x_count, cudaStream_t stream) {
-  using C = TileCfg<L, CTAS>;
+  using C = TileCfg<L, CELLS, CTAS>;
+  constexpr int kTileCells = CELLS, kTileThreads = TileDims<CELLS>::kThreads;
   static int sm_counts[64] = {0};  // per device: the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
   int dev = 0;
   XLBN_CUDA_OK(cudaGetDevice(&dev));
@@ -348,7 +358,7 @@ int launch_step_tile(const StepParams<__half>& p, int x_count, cudaStream_t stre
   if (sm_counts[dev] == 0) {
     int n = 0;
     XLBN_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    XLBN_CUDA_OK(cudaFuncSetAttribute(step_tile_kernel<L, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    XLBN_CUDA_OK(cudaFuncSetAttribute(step_tile_kernel<L, CELLS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     sm_counts[dev] = n;
   }
   const int sm_count = sm_counts[dev];
@@ -357,7 +367,7 @@ int launch_step_tile(const StepParams<__half>& p, int x_count, cudaStream_t stre
   if (n_tiles > 0x7fffffffLL) return fail(XLBN_E_SHAPE, "tile kernel: %lld tiles", n_tiles);
   const long long resident = (long long)CTAS * sm_count;
   const int grid = (int)(n_tiles < resident ? n_tiles : resident);  // persistent: CTAS CTAs per SM walk the tiles round-robin
-  step_tile_kernel<L, CTAS><<<grid, kTileThreads, C::kSmemBytes, stream>>>(p, (int)n_tiles, rows, tiles_per_plane);
+  step_tile_kernel<L, CELLS, CTAS><<<grid, kTileThreads, C::kSmemBytes, stream>>>(p, (int)n_tiles, rows, tiles_per_plane);
   XLBN_LAUNCH_OK("step_tile_kernel launch");
   return 0;
 }
