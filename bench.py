@@ -244,6 +244,8 @@ def roofline_of(args, shape, world, ms_per_step):
                 out["traffic"] = entry["bytes"] if isinstance(entry, dict) else entry
                 if isinstance(entry, dict):
                     out["traffic_source"] = entry.get("source")
+                    if entry.get("kernel"):  # the kernel the capture saw for this workload (the library picks it: csrc/step_kernel.cuh launch_step_base)
+                        out["kernel"] = "xlbn::" + entry["kernel"].replace("void ", "").strip()
         except Exception:
             pass
     return out

@@ -104,7 +104,11 @@ typedef struct xlbn_stepper_desc {
                                402 = FP32FP16 BGK only: the persistent TMA-fed tile kernel (csrc/step_tile.cuh), what 0 selects where the
                                      slab can be tiled: 1024-cell tiles if they fit the plane, else 512-cell tiles;
                                      404 = 512-cell tiles; 403 = 512-cell tiles at three CTAs per SM (tuning variant).
-                                     Needs nz | 512, nz % 8 == 0, ny % (512 / nz) == 0, no halo handle on the call */
+                                     Needs nz | 512, nz % 8 == 0, ny % (512 / nz) == 0, no halo handle on the call
+                               501 = BGK with fp32 storage (FP32FP32, FP64FP32), 3-D lattices: the scalar tile kernel — the same TMA-fed
+                                     persistent pipeline with one cell per consumer thread (512-cell tiles, one CTA per SM); what 0
+                                     selects for D3Q19 FP32FP32 where the slab can be tiled.  502 = two CTAs per SM (fp32 compute only).
+                                     Needs nz | 512, nz % 16 == 0, ny % (512 / nz) == 0, no halo handle on the call */
   const xlbn_bc_desc* bcs;  /* n_bc entries, copied */
 } xlbn_stepper_desc;
 

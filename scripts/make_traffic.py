@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SOURCES = {  # key -> raw page
-    "cavity_D3Q19_BGK_FP32FP32_512x512x512": "r2_ncu_full_step_kernel_d3q19_f32_raw.csv",
+    "cavity_D3Q19_BGK_FP32FP32_512x512x512": "r2_ncu_tile1_d3q19_f32_raw.csv",
     "cavity_D3Q19_BGK_FP32FP16_512x512x512": "r2_ncu_tile_final_raw.csv",
     "cavity_D3Q27_KBC_FP32FP32_512x512x512": "r2_ncu_full_step_kernel_d3q27_kbc_lean_512_raw.csv",
     "cavity_D3Q27_KBC_FP32FP32_256x256x256": "r2_ncu_full_step_kernel_d3q27_kbc_lean_raw.csv",

@@ -144,6 +144,46 @@ def test_tile_kernel_is_bit_identical_to_the_reference_kernel(lattice, shape, wa
         assert np.array_equal(f, ref), f"cells_per_thread={v}: {int((f != ref).sum())} of {f.size} values differ from the reference kernel's, rel err {rel_err(f, ref):.3e}"
 
 
+TILE1_SHAPES = [("D3Q19", (3, 4, 512), True), ("D3Q19", (4, 8, 128), True), ("D3Q27", (3, 32, 64), True), ("D3Q19", (2, 64, 16), False), ("D3Q27", (5, 2, 256), False),
+                ("D3Q19", (1, 32, 16), True), ("D3Q19", (40, 64, 64), True), ("D3Q27", (33, 32, 128), True), ("D3Q19", (149, 16, 32), True)]  # fmt: skip
+
+
+@pytest.mark.parametrize("policy", ["FP32FP32", "FP64FP32"])
+@pytest.mark.parametrize("lattice,shape,walls", TILE1_SHAPES)
+def test_scalar_tile_kernel_is_bit_identical_to_the_reference_kernel(lattice, shape, walls, policy):
+    """cells_per_thread 501 / 502: the TMA-fed tile pipeline around the per-cell code of the direct kernel (one cell per consumer thread),
+    fp32 storage with fp32 or fp64 arithmetic: every population equal to the C restatement of the reference kernel and to the direct kernel."""
+    g = tile_case(lattice, shape, 12, 13, walls, policy)
+    ref, _, _ = c_oracle_run(g)
+    for v in (501, 502, 1):
+        f, _, _ = native_run(g, cells_per_thread=v)
+        assert np.array_equal(f, ref), f"cells_per_thread={v}: {int((f != ref).sum())} of {f.size} values differ from the reference kernel's, rel err {rel_err(f, ref):.3e}"
+
+
+def test_scalar_tile_kernel_with_every_boundary_kind_and_solid_cells():
+    from oracle import lbm_numpy as O
+
+    g0 = load_golden("warp_sphere_d3q19_bgk_fp32fp16")
+    shape = (48, 32, 64)
+    lat = O.Lattice("D3Q19")
+    box, bne = O.bounding_box_indices(shape), O.bounding_box_indices(shape, remove_edges=True)
+    walls = np.unique(np.concatenate([box[k] for k in ("bottom", "top", "front", "back")], axis=1), axis=-1)
+    X, Y, Z = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+    body = np.array(np.where((X - 12) ** 2 + (Y - 16) ** 2 + (Z - 32) ** 2 < 30))
+    pv = np.zeros((3, shape[1], shape[2]), np.float32)
+    pv[0] = 0.03
+    for policy in ("FP32FP32", "FP64FP32"):
+        g = dict(g0)
+        g.update(shape=shape, steps=40, policy=policy, f_init=O.initialize_eq(shape, lat, policy))
+        g["bcs"] = [dict(kind="fullway", id=1, indices=walls), dict(kind="regularized", id=2, indices=bne["left"], bc_type="velocity", prescribed=pv),
+                    dict(kind="outflow", id=3, indices=bne["right"]), dict(kind="halfway", id=4, indices=body)]  # fmt: skip
+        g["solid255"] = np.array([[12], [16], [32]])
+        ref, _, _ = c_oracle_run(g)
+        for v in (501, 1):
+            f, _, _ = native_run(g, cells_per_thread=v)
+            assert np.array_equal(f, ref), f"{policy} cells_per_thread={v}: {int((f != ref).sum())} of {f.size} values differ, rel err {rel_err(f, ref):.3e}"
+
+
 def test_tile_kernel_with_every_boundary_kind_and_solid_cells():
     """Regularized inlet, ExtrapolationOutflow outlet, Halfway body, Fullway walls and cells with id 255 inside the tile path."""
     from oracle import lbm_numpy as O

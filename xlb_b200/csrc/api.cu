@@ -106,7 +106,7 @@ int xlbn_stepper_create(const xlbn_stepper_desc* desc, xlbn_stepper** out) {
   if (desc->compute_dtype == XLBN_F32 && desc->store_dtype == XLBN_F64) return fail(XLBN_E_DTYPE, "stepper_create: no FP32FP64 policy");
   if (desc->n_bc < 0 || (desc->n_bc > 0 && !desc->bcs)) return fail(XLBN_E_ARG, "stepper_create: bad BC list");
   const int cpt = desc->cells_per_thread;
-  if (cpt != 0 && cpt != 1 && cpt != 2 && cpt != 4 && cpt != 8 && cpt != 102 && cpt != 104 && cpt != 202 && cpt != 203 && cpt != 300 && cpt != 301 && cpt != 402 && cpt != 403 && cpt != 404)
+  if (cpt != 0 && cpt != 1 && cpt != 2 && cpt != 4 && cpt != 8 && cpt != 102 && cpt != 104 && cpt != 202 && cpt != 203 && cpt != 300 && cpt != 301 && cpt != 402 && cpt != 403 && cpt != 404 && cpt != 501 && cpt != 502)
     return fail(XLBN_E_ARG, "stepper_create: cells_per_thread = %d", cpt);
   if ((cpt == 300 || cpt == 301) && desc->collision != XLBN_KBC)
     return fail(XLBN_E_ARG, "stepper_create: cells_per_thread = %d selects a KBC formulation; the stepper's collision is %d", cpt, desc->collision);

@@ -900,6 +900,28 @@ int launch_step_base(const StepParams<TS>& p, int x_count, int requested_v, cons
     if (req == 402 || req == 403 || req == 404) return fail(XLBN_E_ARG, "cells_per_thread = %d: the tile kernel exists for FP32FP16 BGK on 3-D lattices only", req);
   }
 #endif
+#if !XLBN_ON_HOST
+  // 501 / 502: the scalar tile kernel (step_tile.cuh: one cell per consumer thread, TMA-fed, persistent) with one / two CTAs per SM.
+  // Built for the BGK operators with fp32 storage (FP32FP32, FP64FP32) on the 3-D lattices.
+  // It is the default for D3Q19 BGK FP32FP32 wherever the slab can be tiled: 512^3 cavity 1.02 of the measured copy bandwidth against 0.98
+  // for the direct-load kernel, 256^3 1.005 against 0.96 (profiles/r2_call13_matrix.txt).  D3Q27 (issue-bound with 16 warps: 0.87 against
+  // 1.00) and FP64FP32 (0.72 against 0.71) keep the direct kernel unless asked.
+  if constexpr (COLL == XLBN_BGK && sizeof(TS) == 4 && sizeof(TC) == 4 && L::D == 3 && L::Q == 19) {
+    if (requested_v == 0 && tile1_eligible<L, TS>(p, f0, f1, g0, g1, o0 != nullptr || o1 != nullptr)) req = 501;
+  }
+  if (req == 501 || req == 502) {
+    if constexpr (COLL == XLBN_BGK && sizeof(TS) == 4 && L::D == 3) {
+      if (!tile1_eligible<L, TS>(p, f0, f1, g0, g1, o0 != nullptr || o1 != nullptr))
+        return fail(XLBN_E_SHAPE, "cells_per_thread = %d: the scalar tile kernel needs nz | 512, nz %% 16 == 0, ny %% (512 / nz) == 0, 16-byte aligned arrays and no halo handle (nz = %d, ny = %d)", req, p.nz, p.ny);
+      if constexpr (sizeof(TC) == 4) {
+        if (req == 502) return launch_step_tile1<L, COLL, TC, TS, 2>(p, x_count, stream);
+      }
+      return launch_step_tile1<L, COLL, TC, TS, 1>(p, x_count, stream);
+    } else {
+      return fail(XLBN_E_ARG, "cells_per_thread = %d: the scalar tile kernel is built for BGK with fp32 storage on 3-D lattices", req);
+    }
+  }
+#endif
   if (req == 202 || req == 203) {
     if constexpr (can_h2) {
       if (pick_cells_per_thread(2, 1, (int)sizeof(TS), p.nz, p.bc, {f0, f1, g0, g1, o0, o1}) == 2) {

@@ -86,7 +86,8 @@ struct TileGeom {
   unsigned cell0;  // element offset of its first cell inside a population
 };
 
-XLBN_DEVFN inline TileGeom tile_geom(const StepParams<__half>& p, int tile, int rows, int tiles_per_plane) {
+template <class TS>
+XLBN_DEVFN inline TileGeom tile_geom(const StepParams<TS>& p, int tile, int rows, int tiles_per_plane) {
   TileGeom g;
   g.x = p.x_begin + tile / tiles_per_plane;
   g.y0 = (tile % tiles_per_plane) * rows;
@@ -96,10 +97,10 @@ XLBN_DEVFN inline TileGeom tile_geom(const StepParams<__half>& p, int tile, int 
 
 // Where population l of a tile comes from: up to two contiguous runs (elements), in the order they are laid out in the stage row.
 // (cx, cy) = kernel-axis velocity components of population l: the producer lane looks them up once, before its tile loop.
-template <class L>
-XLBN_DEVFN int tile_plan(const StepParams<__half>& p, int l, int cx, int cy, const TileGeom& g, int rows, const __half* (&src)[2], unsigned (&dst)[2], unsigned (&count)[2]) {
+template <class L, class TS>
+XLBN_DEVFN int tile_plan(const StepParams<TS>& p, int l, int cx, int cy, const TileGeom& g, int rows, const TS* (&src)[2], unsigned (&dst)[2], unsigned (&count)[2]) {
   const int tab = (cx == 1 && g.x == 0) ? 1 : ((cx == -1 && g.x == p.nx - 1) ? 2 : 0);  // ghost plane / periodic wrap in x (fill_step_params)
-  const __half* base = p.pull[tab][l] + (unsigned)g.x * (unsigned)p.plane;
+  const TS* base = p.pull[tab][l] + (unsigned)g.x * (unsigned)p.plane;
   const unsigned nz = (unsigned)p.nz;
   const int ys = g.y0 - cy;  // first source row: pull from y - c_y (stream.py:66-78)
   if (ys < 0) {  // row ny-1, then rows 0 .. rows-2
@@ -129,6 +130,46 @@ XLBN_DEVFN int tile_plan(const StepParams<__half>& p, int l, int cx, int cy, con
   dst[0] = 0;
   count[0] = (unsigned)rows * nz;
   return 1;
+}
+
+// The same plan as scalars (no local arrays, no run-time indexing): run 0 = n0 elements from src0 to the start of the stage row, run 1 =
+// n1 elements (0: none) from src1 right behind it.  The scalar tile kernel uses this form: ptxas 12.9 merged dst[] and count[] of
+// tile_plan in that kernel's D3Q19 instantiation (wrong destination offsets on the wrapped rows; caught by the bit-identity tests).
+template <class TS>
+struct TileRuns {
+  const TS *src0, *src1;
+  unsigned n0, n1;
+};
+
+template <class L, class TS>
+XLBN_DEVFN TileRuns<TS> tile_runs(const StepParams<TS>& p, int l, int cx, int cy, const TileGeom& g, int rows) {
+  const int tab = (cx == 1 && g.x == 0) ? 1 : ((cx == -1 && g.x == p.nx - 1) ? 2 : 0);  // ghost plane / periodic wrap in x (fill_step_params)
+  const TS* base = p.pull[tab][l] + (unsigned)g.x * (unsigned)p.plane;
+  const unsigned nz = (unsigned)p.nz, all = (unsigned)rows * nz;
+  const int ys = g.y0 - cy;  // first source row: pull from y - c_y (stream.py:66-78)
+  TileRuns<TS> r;
+  if (ys < 0) {  // row ny-1, then rows 0 .. rows-2
+    r.src0 = base + (unsigned)(p.ny - 1) * nz;
+    r.n0 = nz;
+    r.src1 = base;
+    r.n1 = all - nz;
+  } else if (ys + rows > p.ny) {  // rows ys .. ny-1, then row 0
+    r.src0 = base + (unsigned)ys * nz;
+    r.n0 = all - nz;
+    r.src1 = base;
+    r.n1 = nz;
+    if (r.n0 == 0) {  // a one-row tile: row 0 is all of it
+      r.src0 = base;
+      r.n0 = nz;
+      r.n1 = 0;
+    }
+  } else {
+    r.src0 = base + (unsigned)ys * nz;
+    r.n0 = all;
+    r.src1 = base;
+    r.n1 = 0;
+  }
+  return r;
 }
 
 // two half2 words -> (hi half of a, lo half of b): the pair one element to the right of a / to the left of b
@@ -318,7 +359,7 @@ __global__ void __launch_bounds__(TileDims<CELLS>::kThreads, CTAS) step_tile_ker
       if (lane < L::Q) {
         const __half* src[2];
         unsigned dst[2], count[2];
-        const int n = tile_plan<L>(p, lane, pcx, pcy, g, rows, src, dst, count);
+        const int n = tile_plan<L, __half>(p, lane, pcx, pcy, g, rows, src, dst, count);
         for (int i = 0; i < n; ++i) bulk_load(stage + lane * kTileRowBytes + dst[i] * 2u, src[i], count[i] * 2u, full + s);
       } else if (lane == L::Q) {
         bulk_load(stage + L::Q * kTileRowBytes, p.bc + g.cell0, kTileCells, full + s);
@@ -369,6 +410,147 @@ int launch_step_tile(const StepParams<__half>& p, int x_count, cudaStream_t stre
   const int grid = (int)(n_tiles < resident ? n_tiles : resident);  // persistent: CTAS CTAs per SM walk the tiles round-robin
   step_tile_kernel<L, CELLS, CTAS><<<grid, kTileThreads, C::kSmemBytes, stream>>>(p, (int)n_tiles, rows, tiles_per_plane);
   XLBN_LAUNCH_OK("step_tile_kernel launch");
+  return 0;
+}
+
+// ---- the scalar tile kernel: ONE cell per consumer thread, any collision, any precision policy -------------------------------------
+// The same pipeline (producer warp, bulk copies into a ring of stages, 16 consumer warps that never meet at a CTA barrier, direct
+// stores) around the per-cell code of the direct kernel: the pulled populations come out of shared memory instead of 19 / 27 global loads
+// with 64-bit address arithmetic, everything after that is step_body's — input-side EquilibriumBC, collide_in_step, the scalar boundary
+// routine.  A tile is 512 cells; z rotation = one shifted LDS per population.  Persistent, so a small grid has no tail of partial waves.
+constexpr int kT1Cells = 512, kT1Threads = kT1Cells + 32;
+
+template <class L, class TS, int CTAS>
+struct Tile1Cfg {
+  static constexpr int kInBytes = L::Q * kT1Cells * (int)sizeof(TS) + kT1Cells;
+  static constexpr int kMaxStages = (227 * 1024 / CTAS - 1024 - kTileBarBytes) / kInBytes;
+  static constexpr int kInStages = kMaxStages > 4 ? 4 : kMaxStages;
+  static constexpr int kSmemBytes = kTileBarBytes + kInStages * kInBytes;
+  static_assert(kInStages >= 2, "at least double buffering");
+};
+
+template <class L, int COLL, class TC, class TS, int CTAS>
+__global__ void __launch_bounds__(kT1Threads, CTAS) step_tile1_kernel(const __grid_constant__ StepParams<TS> p, const int n_tiles, const int rows, const int tiles_per_plane) {
+  using namespace tile_ptx;
+  using C = Tile1Cfg<L, TS, CTAS>;
+  constexpr int Q = L::Q;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + C::kInStages;
+  TileGeom* geoms = reinterpret_cast<TileGeom*>(smem + 64);
+  unsigned char* in0 = smem + kTileBarBytes;
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < C::kInStages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, kT1Cells / 32);
+    }
+    mbar_init_fence();
+  }
+  __syncthreads();
+
+  if (warp == kT1Cells / 32) {  // producer
+    const int pl = lane < Q ? lane : 0, pcx = L::ck(0, pl), pcy = L::ck(1, pl);
+    int k = 0;
+    for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++k) {
+      const int s = k % C::kInStages;
+      const uint32_t phase = (uint32_t)(k / C::kInStages) & 1u;
+      mbar_wait(empty + s, phase ^ 1u);
+      const TileGeom g = tile_geom(p, tile, rows, tiles_per_plane);
+      unsigned char* stage = in0 + s * C::kInBytes;
+      if (lane == 0) {
+        geoms[s] = g;
+        mbar_expect_tx(full + s, (uint32_t)C::kInBytes);
+      }
+      __syncwarp();
+      if (lane < Q) {
+        const TileRuns<TS> r = tile_runs<L, TS>(p, lane, pcx, pcy, g, rows);
+        unsigned char* row = stage + (unsigned)lane * (unsigned)(kT1Cells * sizeof(TS));
+        bulk_load(row, r.src0, r.n0 * (unsigned)sizeof(TS), full + s);
+        if (r.n1) bulk_load(row + r.n0 * (unsigned)sizeof(TS), r.src1, r.n1 * (unsigned)sizeof(TS), full + s);
+      } else if (lane == Q) {
+        bulk_load(stage + Q * kT1Cells * sizeof(TS), p.bc + g.cell0, kT1Cells, full + s);
+      }
+    }
+    return;
+  }
+
+  // consumers
+  const unsigned nz = (unsigned)p.nz;
+  const TC omega = (TC)p.omega;
+  int k = 0;
+  for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++k) {
+    const int s = k % C::kInStages;
+    const uint32_t phase = (uint32_t)(k / C::kInStages) & 1u;
+    const unsigned char* stage = in0 + s * C::kInBytes;
+    const TS* in = reinterpret_cast<const TS*>(stage);
+    const unsigned t = ((unsigned)tid + 32u * (unsigned)(k & (kT1Cells / 32 - 1))) & (unsigned)(kT1Cells - 1);  // warps take turns with the row ends
+    const unsigned z = t & (nz - 1u);
+    const unsigned tm = (z == 0u) ? t + nz - 1u : t - 1u;       // source of c_z = +1 populations: element z - 1 of the same row
+    const unsigned tp = (z + 1u == nz) ? t + 1u - nz : t + 1u;  // source of c_z = -1 populations
+    mbar_wait(full + s, phase);
+    const TileGeom g = geoms[s];
+    TC f[1][Q];
+    XLBN_FOR(Q, l)
+      constexpr int cz = L::ck(2, l);
+      f[0][l] = Cvt<TC, TS>::up(in[l * kT1Cells + (cz == 1 ? tm : (cz == -1 ? tp : t))]);
+    XLBN_END
+    Pack<uint8_t, 1> ids;
+    ids.v[0] = stage[Q * kT1Cells * sizeof(TS) + t];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+    const int id = ids.v[0];
+    if (id == 255) continue;  // nse_stepper.py:356-358
+    const unsigned cell = g.cell0 + t;
+    bool tail = id != 0;
+    if (tail) {  // EquilibriumBC at the input side (StepParams::eq_in)
+      int slot = -1;
+#pragma unroll
+      for (int i = 0; i < kEqSlots; ++i)
+        if (p.eq_ids[i] == id) slot = i;
+      if (slot >= 0) {
+        XLBN_FOR(Q, l) f[0][l] = (TC)p.eq_in[slot][l]; XLBN_END
+        tail = false;
+      }
+    }
+    if (!tail) {
+      collide_in_step<L, COLL, TC, TS>(p, f[0], omega);
+    } else {
+      const int y = g.y0 + (int)(t / nz);
+      bc_compute<L, COLL, TC, TS, 1>(p, ids, g.x, y, (int)z, f);
+    }
+    store_cells<L, TC, TS, 1, 0, false>(p, cell, ids, f);
+  }
+}
+
+template <class L, class TS>
+bool tile1_eligible(const StepParams<TS>& p, const void* f0, const void* f1, const void* ghost_lo, const void* ghost_hi, bool has_peers) {
+  auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % 16) == 0; };
+  if (has_peers || p.nz < 8 || p.nz > kT1Cells || (kT1Cells % p.nz) != 0 || ((p.nz * (int)sizeof(TS)) % 16) != 0 || (p.nz % 16) != 0) return false;
+  if (p.ny % (kT1Cells / p.nz) != 0) return false;
+  return aligned(f0) && aligned(f1) && aligned(ghost_lo) && aligned(ghost_hi) && aligned(p.bc);
+}
+
+template <class L, int COLL, class TC, class TS, int CTAS>
+int launch_step_tile1(const StepParams<TS>& p, int x_count, cudaStream_t stream) {
+  using C = Tile1Cfg<L, TS, CTAS>;
+  static int sm_counts[64] = {0};
+  int dev = 0;
+  XLBN_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(XLBN_E_STATE, "tile kernel: device ordinal %d", dev);
+  if (sm_counts[dev] == 0) {
+    int n = 0;
+    XLBN_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    XLBN_CUDA_OK(cudaFuncSetAttribute(step_tile1_kernel<L, COLL, TC, TS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    sm_counts[dev] = n;
+  }
+  const int rows = kT1Cells / p.nz, tiles_per_plane = p.ny / rows;
+  const long long n_tiles = (long long)tiles_per_plane * x_count;
+  if (n_tiles > 0x7fffffffLL) return fail(XLBN_E_SHAPE, "tile kernel: %lld tiles", n_tiles);
+  const long long resident = (long long)CTAS * sm_counts[dev];
+  const int grid = (int)(n_tiles < resident ? n_tiles : resident);
+  step_tile1_kernel<L, COLL, TC, TS, CTAS><<<grid, kT1Threads, C::kSmemBytes, stream>>>(p, (int)n_tiles, rows, tiles_per_plane);
+  XLBN_LAUNCH_OK("step_tile1_kernel launch");
   return 0;
 }
 #endif  // !XLBN_ON_HOST

@@ -183,6 +183,12 @@ class IncompressibleNavierStokesStepper(Stepper):
 
     # -- one time step -----------------------------------------------------------------------------------------------------
     def _step(self, f_0, f_1, bc_mask, missing_mask, omega, timestep):
+        # Fields are torch.Tensor subclasses (field.py): outside this guard every .shape / .dtype / .data_ptr() below goes through
+        # __torch_function__ (3-8 us each, ~75 us per call — more than a whole 128^3 time step on the device)
+        with torch._C.DisableTorchFunctionSubclass():
+            return self._step_checked(f_0, f_1, bc_mask, missing_mask, omega, timestep)
+
+    def _step_checked(self, f_0, f_1, bc_mask, missing_mask, omega, timestep):
         vs = self.velocity_set
         for name, t in (("f_0", f_0), ("f_1", f_1), ("bc_mask", bc_mask)):
             native.require_cuda(t, name)
@@ -261,7 +267,13 @@ class IncompressibleNavierStokesStepper(Stepper):
             return f_1, f_0
         return f_0, f_1
 
-    def run_streamed(self, host_f, host_out, f_0, f_1, bc_mask, missing_mask, omega, n_steps, host_bc_mask=None, host_missing_mask=None, chunk_planes=32):
+    def run_streamed(self, *args, **kwargs):
+        with torch._C.DisableTorchFunctionSubclass():  # see _step
+            return self._run_streamed(*args, **kwargs)
+
+    run_streamed.__doc__ = "See _run_streamed (same arguments)."
+
+    def _run_streamed(self, host_f, host_out, f_0, f_1, bc_mask, missing_mask, omega, n_steps, host_bc_mask=None, host_missing_mask=None, chunk_planes=32):
         """A whole HOST-RESIDENT job — upload, ``n_steps`` time steps, download — as one pipeline over x-planes.
 
         ``host_f`` (pinned, [q, nx, ny, nz], store dtype) holds the populations at step 0, ``host_out`` (pinned, same shape) receives
