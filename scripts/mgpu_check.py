@@ -105,6 +105,8 @@ def main():
         ("cavity2d", (16 * world, 40), "D2Q9", "FP32FP32", "BGK", 40),
         ("cavity2d", (16 * world, 40), "D2Q9", "FP32FP32", "KBC", 40),
         ("cavity", (8 * world, 16, 64), "D3Q19", "FP32FP16", "BGK", 25),  # tile-kernel shape (nz | 512): interior planes take the tile path
+        ("cavity", (8 * world, 16, 64), "D3Q19", "FP32FP32", "BGK", 25),  # ... the scalar tile kernel (fp32 storage)
+        ("cavity", (8 * world, 16, 64), "D3Q19", "FP64FP32", "BGK", 25),
     ]
     for case, shape, lattice, policy, collision, steps in cases:
         f, bc, mm = run(case, shape, lattice, policy, collision, steps, None)

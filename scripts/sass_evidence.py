@@ -11,9 +11,10 @@ import sys
 
 BUILD = sys.argv[1] if len(sys.argv) > 1 else "/tmp/xlb_b200_build"
 KERNELS = [  # (title, object, mangled-name fragment)
-    ("D3Q19 BGK FP32FP32, one cell per thread (the headline kernel)", "step_inst_d3q19_bgk.o", "step_kernelINS_7LatticeINS_9D3Q19BaseEEELi0EffLi1ELi0EEEv"),
+    ("D3Q19 BGK FP32FP32, scalar tile kernel (TMA-fed, persistent, one cell per thread): the headline kernel", "step_inst_d3q19_bgk.o", "step_tile1_kernelINS_7LatticeINS_9D3Q19BaseEEELi0EffLi1EEEv"),
+    ("D3Q19 BGK FP32FP32, direct-load kernel, one cell per thread (slab faces, shapes that cannot be tiled)", "step_inst_d3q19_bgk.o", "step_kernelINS_7LatticeINS_9D3Q19BaseEEELi0EffLi1ELi0EEEv"),
     ("D3Q19 BGK FP32FP16, half2-state pair path (direct loads)", "step_inst_d3q19_bgk.o", "step_kernelINS_7LatticeINS_9D3Q19BaseEEELi0Ef6__halfLi2ELi2EEEv"),
-    ("D3Q19 BGK FP32FP16, tile kernel (TMA-fed, persistent), 2 CTAs/SM", "step_inst_d3q19_bgk.o", "step_tile_kernelINS_7LatticeINS_9D3Q19BaseEEELi2EEEv"),
+    ("D3Q19 BGK FP32FP16, tile kernel (TMA-fed, persistent), 1024-cell tiles, 1 CTA/SM", "step_inst_d3q19_bgk.o", "step_tile_kernelINS_7LatticeINS_9D3Q19BaseEEELi1024ELi1EEEv"),
     ("D3Q27 KBC FP32FP32, register-lean formulation (default)", "step_inst_kbc_lean.o", "step_kernelINS_7LatticeINS_9D3Q27BaseEEELi9EffLi1ELi0EEEv"),
 ]
 
@@ -60,7 +61,14 @@ def straight_path(lines):
             start = i + 1
     good = [g for g in segs if sum("STG" in x for x in g) >= 9 and sum(("LDG" in x or "LDS" in x) for x in g) >= 9]
     if not good:
-        return []
+        # persistent kernels: the loads (LDS out of the stage) and the stores of the loop body can sit in different stretches; take the
+        # stretch with the most population loads and the cheapest stretch with a full set of stores, in program order
+        loads = max(segs, key=lambda g: sum(("LDS" in x or "LDG" in x) for x in g), default=[])
+        stores = [g for g in segs if sum("STG" in x for x in g) >= 9]
+        if not stores or loads is None:
+            return []
+        st = min(stores, key=lambda g: (sum(("STL" in x or "LDL" in x) for x in g), len(g)))
+        return loads + ([] if st is loads else st)
     return min(good, key=lambda g: (sum(("STL" in x or "LDL" in x) for x in g), len(g)))
 
 

@@ -85,6 +85,21 @@ def test_slab_run_is_bit_identical(name, n_slabs, split_faces):
 
 
 @pytest.mark.parametrize("n_slabs", [2, 4])
+@pytest.mark.parametrize("policy", ["FP32FP32", "FP64FP32", "FP32FP16"])
+@pytest.mark.parametrize("walls", [True, False])
+def test_slab_run_with_tile_kernel_interiors_is_bit_identical(policy, n_slabs, walls):
+    """Shapes the tile kernels accept (csrc/step_tile.cuh): the interior launch of every slab (no halo handle on that call) takes the TMA-fed
+    tile kernel on the partial x range [1, nxl - 1), the two face planes the direct kernel with peer stores; together they must give the
+    bits of the undecomposed run (which tiles the whole box)."""
+    from common import native_run, tile_case
+
+    g = tile_case("D3Q19", (16, 16, 64), 12, 17, walls, policy)
+    whole, _, _ = native_run(g)
+    parts = run_slabs(g, n_slabs, g["steps"], True)
+    assert np.array_equal(parts, whole)
+
+
+@pytest.mark.parametrize("n_slabs", [2, 4])
 @pytest.mark.parametrize("split_faces", [False, True])
 @pytest.mark.parametrize("name", ["cavity_d2q9_bgk_fp32", "cavity_d2q9_kbc_fp32", "channel2d_d2q9_bgk_outflow_fp32", "channel2d_d2q9_bgk_zouhe_pressure_fp32"])
 def test_2d_slab_run_is_bit_identical(name, n_slabs, split_faces):

@@ -903,10 +903,10 @@ int launch_step_base(const StepParams<TS>& p, int x_count, int requested_v, cons
 #if !XLBN_ON_HOST
   // 501 / 502: the scalar tile kernel (step_tile.cuh: one cell per consumer thread, TMA-fed, persistent) with one / two CTAs per SM.
   // Built for the BGK operators with fp32 storage (FP32FP32, FP64FP32) on the 3-D lattices.
-  // It is the default for D3Q19 BGK FP32FP32 wherever the slab can be tiled: 512^3 cavity 1.02 of the measured copy bandwidth against 0.98
-  // for the direct-load kernel, 256^3 1.005 against 0.96 (profiles/r2_call13_matrix.txt).  D3Q27 (issue-bound with 16 warps: 0.87 against
-  // 1.00) and FP64FP32 (0.72 against 0.71) keep the direct kernel unless asked.
-  if constexpr (COLL == XLBN_BGK && sizeof(TS) == 4 && sizeof(TC) == 4 && L::D == 3 && L::Q == 19) {
+  // It is the default for D3Q19 BGK with fp32 storage wherever the slab can be tiled: FP32FP32 512^3 cavity 1.03 of the measured copy
+  // bandwidth against 0.98 for the direct-load kernel, 256^3 1.00 against 0.96, 128^3 0.88 against 0.87; FP64FP32 0.74 against 0.71
+  // (profiles/r2_call13_matrix.txt, r2_call15_matrix.txt).  D3Q27 (issue-bound with 16 warps: 0.87 against 1.00) keeps the direct kernel.
+  if constexpr (COLL == XLBN_BGK && sizeof(TS) == 4 && L::D == 3 && L::Q == 19) {
     if (requested_v == 0 && tile1_eligible<L, TS>(p, f0, f1, g0, g1, o0 != nullptr || o1 != nullptr)) req = 501;
   }
   if (req == 501 || req == 502) {

@@ -513,12 +513,13 @@ __global__ void __launch_bounds__(kT1Threads, CTAS) step_tile1_kernel(const __gr
         tail = false;
       }
     }
-    if (!tail) {
+    if (!tail) {  // the straight-line path ends here, so that its register allocation is independent of the boundary code (as in step_body)
       collide_in_step<L, COLL, TC, TS>(p, f[0], omega);
-    } else {
-      const int y = g.y0 + (int)(t / nz);
-      bc_compute<L, COLL, TC, TS, 1>(p, ids, g.x, y, (int)z, f);
+      store_cells<L, TC, TS, 1, 0, false>(p, cell, ids, f);
+      continue;
     }
+    const int y = g.y0 + (int)(t / nz);
+    bc_compute<L, COLL, TC, TS, 1>(p, ids, g.x, y, (int)z, f);
     store_cells<L, TC, TS, 1, 0, false>(p, cell, ids, f);
   }
 }
