@@ -127,8 +127,44 @@ int host_step_tile(const StepCall& c) {
   return 0;
 }
 
+// The scalar tile kernel (cells_per_thread 501): copy plan as scalars (tile_runs) executed with memcpy, then the 512 consumer threads of
+// the tile one after the other (tile1_load + tile1_finish: the shipped per-thread code).
+template <class L, int COLL, class TC, class TS>
+int host_step_tile1(const StepCall& c) {
+  StepParams<TS> p;
+  if (int e = fill_step_params<L, TS>(c, p)) return e;
+  if (!tile1_eligible<L, TS>(p, c.f0, c.f1, c.ghost_lo, c.ghost_hi, c.out_lo != nullptr || c.out_hi != nullptr)) return fail(XLBN_E_SHAPE, "mirror: shape not eligible for the scalar tile kernel");
+  const int rows = kT1Cells / p.nz, tiles_per_plane = p.ny / rows, n_tiles = tiles_per_plane * c.x_count;
+  static TS in[L::Q * kT1Cells];
+  static unsigned char id_row[kT1Cells];
+  const unsigned nz = (unsigned)p.nz;
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const TileGeom g = tile_geom(p, tile, rows, tiles_per_plane);
+    memset(in, 0xff, sizeof(in));
+    for (int l = 0; l < L::Q; ++l) {  // the producer warp, lane l
+      const TileRuns<TS> r = tile_runs<L, TS>(p, l, L::ck(0, l), L::ck(1, l), g, rows);
+      if (r.n0 + r.n1 != (unsigned)kT1Cells) return fail(XLBN_E_SHAPE, "mirror: copy plan covers %u of 512 elements", r.n0 + r.n1);
+      if ((reinterpret_cast<uintptr_t>(r.src0) % 16) || ((r.n0 * sizeof(TS)) % 16) || (r.n1 && (reinterpret_cast<uintptr_t>(r.src1) % 16))) return fail(XLBN_E_SHAPE, "mirror: bulk copy not 16-byte aligned");
+      memcpy(in + l * kT1Cells, r.src0, r.n0 * sizeof(TS));
+      if (r.n1) memcpy(in + l * kT1Cells + r.n0, r.src1, r.n1 * sizeof(TS));
+    }
+    memcpy(id_row, p.bc + g.cell0, kT1Cells);
+    for (unsigned t = 0; t < (unsigned)kT1Cells; ++t) {  // the consumer threads
+      const unsigned z = t & (nz - 1u);
+      const unsigned tm = (z == 0u) ? t + nz - 1u : t - 1u, tp = (z + 1u == nz) ? t + 1u - nz : t + 1u;
+      TC f[1][L::Q];
+      Pack<uint8_t, 1> ids;
+      tile1_load<L, TC, TS>(in, id_row, t, tm, tp, f, ids);
+      tile1_finish<L, COLL, TC, TS>(p, g, t, z, (TC)p.omega, f, ids);
+    }
+  }
+  return 0;
+}
+
 template <class L, int COLL, class TC, class TS>
 int host_step_v(const StepCall& c) {
+  if constexpr (COLL == XLBN_BGK && sizeof(TS) == 4 && L::D == 3)
+    if (c.requested_v == 501) return host_step_tile1<L, COLL, TC, TS>(c);
   if constexpr (COLL == XLBN_BGK && sizeof(TC) == 4 && sizeof(TS) == 2 && L::D == 3)
     if (c.requested_v == 404) return host_step_tile<L, 512>(c);
   if constexpr (COLL == XLBN_BGK && sizeof(TC) == 4 && sizeof(TS) == 2 && L::D == 3)

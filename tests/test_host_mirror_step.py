@@ -37,7 +37,7 @@ SYM = lambda lat, coll: f"mirror_step_{'0x' if lat == 'D2Q9X' else LATTICE[lat]}
 def mirror():
     if shutil.which("nvcc") is None:
         pytest.skip("nvcc not available")
-    deps = [SRC] + [os.path.join(CSRC, h) for h in ("step_kernel.cuh", "lbm_math.cuh", "lattice.cuh", "common.cuh", "error.cu")]
+    deps = [SRC] + [os.path.join(CSRC, h) for h in ("step_kernel.cuh", "step_tile.cuh", "lbm_math.cuh", "lattice.cuh", "common.cuh", "error.cu")]
     if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(d) for d in deps):
         build = os.path.dirname(OUT)
         os.makedirs(build, exist_ok=True)
@@ -263,6 +263,21 @@ def test_tile_kernel_logic_is_bit_identical_to_the_reference_kernel(mirror, latt
     g = tile_case(lattice, shape, 6, 11, walls)
     ref, _, _ = c_oracle_run(g)
     f = mirror_run(mirror, g, v=402 if cells == 1024 else 404)
+    assert np.array_equal(f, ref), f"{int((f != ref).sum())} of {f.size} values differ, rel err {rel_err(f, ref):.3e}"
+
+
+@pytest.mark.parametrize("policy", ["FP32FP32", "FP64FP32"])
+@pytest.mark.parametrize("lattice,shape,walls", [("D3Q19", (3, 4, 512), True), ("D3Q19", (4, 8, 128), True), ("D3Q27", (3, 16, 64), True), ("D3Q19", (2, 64, 16), False),
+                                                 ("D3Q27", (5, 2, 256), False), ("D3Q19", (1, 32, 16), True)])  # fmt: skip
+def test_scalar_tile_kernel_logic_is_bit_identical_to_the_reference_kernel(mirror, lattice, shape, walls, policy):
+    """cells_per_thread 501 (csrc/step_tile.cuh, step_tile1_kernel): the copy plan (tile_runs: y wrap, x wrap, one-row tiles), the shifted
+    reads out of the stage rows and the per-cell code behind them — executed on the host with the bulk copies as memcpy — against the C
+    oracle, bit for bit.  (The D3Q19 instantiation of this kernel is where ptxas once merged two arrays of the array-based plan.)"""
+    from common import c_oracle_run
+
+    g = tile_case(lattice, shape, 6, 13, walls, policy)
+    ref, _, _ = c_oracle_run(g)
+    f = mirror_run(mirror, g, v=501)
     assert np.array_equal(f, ref), f"{int((f != ref).sum())} of {f.size} values differ, rel err {rel_err(f, ref):.3e}"
 
 

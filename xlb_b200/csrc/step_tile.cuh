@@ -298,6 +298,54 @@ bool tile_eligible(const StepParams<__half>& p, const void* f0, const void* f1, 
   return aligned(f0) && aligned(f1) && aligned(ghost_lo) && aligned(ghost_hi) && aligned(p.bc);
 }
 
+// ---- the scalar tile kernel's per-thread code (the kernel itself is further down; tests/host_math/mirror_step.cu runs these on the host) ----
+constexpr int kT1Cells = 512;
+
+// One cell out of a stage: population l of cell t is element t - c_z (inside its row) of stage row l.
+template <class L, class TC, class TS>
+XLBN_DEV void tile1_load(const TS* in, const unsigned char* id_row, unsigned t, unsigned tm, unsigned tp, TC (&f)[1][L::Q], Pack<uint8_t, 1>& ids) {
+  XLBN_FOR(L::Q, l)
+    constexpr int cz = L::ck(2, l);
+    f[0][l] = Cvt<TC, TS>::up(in[l * kT1Cells + (cz == 1 ? tm : (cz == -1 ? tp : t))]);
+  XLBN_END
+  ids.v[0] = id_row[t];
+}
+
+// ... and from there on the per-cell code of the direct kernel (step_body): input-side EquilibriumBC, collision, boundary routine, store.
+template <class L, int COLL, class TC, class TS>
+XLBN_DEV void tile1_finish(const StepParams<TS>& p, const TileGeom& g, unsigned t, unsigned z, TC omega, TC (&f)[1][L::Q], const Pack<uint8_t, 1>& ids) {
+  const int id = ids.v[0];
+  if (id == 255) return;  // nse_stepper.py:356-358
+  const unsigned cell = g.cell0 + t;
+  bool tail = id != 0;
+  if (tail) {  // EquilibriumBC at the input side (StepParams::eq_in)
+    int slot = -1;
+#pragma unroll
+    for (int i = 0; i < kEqSlots; ++i)
+      if (p.eq_ids[i] == id) slot = i;
+    if (slot >= 0) {
+      XLBN_FOR(L::Q, l) f[0][l] = (TC)p.eq_in[slot][l]; XLBN_END
+      tail = false;
+    }
+  }
+  if (!tail) {  // the straight-line path ends here, so that its register allocation is independent of the boundary code (as in step_body)
+    collide_in_step<L, COLL, TC, TS>(p, f[0], omega);
+    store_cells<L, TC, TS, 1, 0, false>(p, cell, ids, f);
+    return;
+  }
+  const int y = g.y0 + (int)(t / (unsigned)p.nz);
+  bc_compute<L, COLL, TC, TS, 1>(p, ids, g.x, y, (int)z, f);
+  store_cells<L, TC, TS, 1, 0, false>(p, cell, ids, f);
+}
+
+template <class L, class TS>
+bool tile1_eligible(const StepParams<TS>& p, const void* f0, const void* f1, const void* ghost_lo, const void* ghost_hi, bool has_peers) {
+  auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % 16) == 0; };
+  if (has_peers || p.nz < 8 || p.nz > kT1Cells || (kT1Cells % p.nz) != 0 || ((p.nz * (int)sizeof(TS)) % 16) != 0 || (p.nz % 16) != 0) return false;
+  if (p.ny % (kT1Cells / p.nz) != 0) return false;
+  return aligned(f0) && aligned(f1) && aligned(ghost_lo) && aligned(ghost_hi) && aligned(p.bc);
+}
+
 #if !XLBN_ON_HOST
 // ---- device-only plumbing: mbarrier, bulk copies, named barrier -------------------------------------------------------------------
 namespace tile_ptx {
@@ -418,7 +466,7 @@ int launch_step_tile(const StepParams<__half>& p, int x_count, cudaStream_t stre
 // stores) around the per-cell code of the direct kernel: the pulled populations come out of shared memory instead of 19 / 27 global loads
 // with 64-bit address arithmetic, everything after that is step_body's — input-side EquilibriumBC, collide_in_step, the scalar boundary
 // routine.  A tile is 512 cells; z rotation = one shifted LDS per population.  Persistent, so a small grid has no tail of partial waves.
-constexpr int kT1Cells = 512, kT1Threads = kT1Cells + 32;
+constexpr int kT1Threads = kT1Cells + 32;
 
 template <class L, class TS, int CTAS>
 struct Tile1Cfg {
@@ -491,45 +539,12 @@ __global__ void __launch_bounds__(kT1Threads, CTAS) step_tile1_kernel(const __gr
     mbar_wait(full + s, phase);
     const TileGeom g = geoms[s];
     TC f[1][Q];
-    XLBN_FOR(Q, l)
-      constexpr int cz = L::ck(2, l);
-      f[0][l] = Cvt<TC, TS>::up(in[l * kT1Cells + (cz == 1 ? tm : (cz == -1 ? tp : t))]);
-    XLBN_END
     Pack<uint8_t, 1> ids;
-    ids.v[0] = stage[Q * kT1Cells * sizeof(TS) + t];
+    tile1_load<L, TC, TS>(in, stage + Q * kT1Cells * sizeof(TS), t, tm, tp, f, ids);
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);
-    const int id = ids.v[0];
-    if (id == 255) continue;  // nse_stepper.py:356-358
-    const unsigned cell = g.cell0 + t;
-    bool tail = id != 0;
-    if (tail) {  // EquilibriumBC at the input side (StepParams::eq_in)
-      int slot = -1;
-#pragma unroll
-      for (int i = 0; i < kEqSlots; ++i)
-        if (p.eq_ids[i] == id) slot = i;
-      if (slot >= 0) {
-        XLBN_FOR(Q, l) f[0][l] = (TC)p.eq_in[slot][l]; XLBN_END
-        tail = false;
-      }
-    }
-    if (!tail) {  // the straight-line path ends here, so that its register allocation is independent of the boundary code (as in step_body)
-      collide_in_step<L, COLL, TC, TS>(p, f[0], omega);
-      store_cells<L, TC, TS, 1, 0, false>(p, cell, ids, f);
-      continue;
-    }
-    const int y = g.y0 + (int)(t / nz);
-    bc_compute<L, COLL, TC, TS, 1>(p, ids, g.x, y, (int)z, f);
-    store_cells<L, TC, TS, 1, 0, false>(p, cell, ids, f);
+    tile1_finish<L, COLL, TC, TS>(p, g, t, z, omega, f, ids);
   }
-}
-
-template <class L, class TS>
-bool tile1_eligible(const StepParams<TS>& p, const void* f0, const void* f1, const void* ghost_lo, const void* ghost_hi, bool has_peers) {
-  auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % 16) == 0; };
-  if (has_peers || p.nz < 8 || p.nz > kT1Cells || (kT1Cells % p.nz) != 0 || ((p.nz * (int)sizeof(TS)) % 16) != 0 || (p.nz % 16) != 0) return false;
-  if (p.ny % (kT1Cells / p.nz) != 0) return false;
-  return aligned(f0) && aligned(f1) && aligned(ghost_lo) && aligned(ghost_hi) && aligned(p.bc);
 }
 
 template <class L, int COLL, class TC, class TS, int CTAS>
