@@ -98,7 +98,8 @@ typedef struct xlbn_stepper_desc {
                                      FullwayBounceBack (same results; a tuning candidate);
                                301 = KBC only: register-lean formulation of the collision, one cell per thread (same algebra
                                      as kbc.py:268-296, feq recomputed per pass instead of held; rounding-level differences).
-                                     This is what 0 selects for an unforced KBC stepper.
+                                     This is what 0 selects for a KBC stepper, ForcedCollision(KBC) included (the ExactDifference
+                                     term is added in the formulation's last pass).
                                300 = KBC only: the literal three-array formulation with the reference's own roundings (IEEE divisions,
                                      nothing fused): bit-identical to the reference kernel; the parity form, ~2x slower
                                402 = FP32FP16 BGK only: the persistent TMA-fed tile kernel (csrc/step_tile.cuh), what 0 selects where the

@@ -29,7 +29,7 @@ COLLISION = {"BGK": 0, "KBC": 1, "SmagorinskyLESBGK": 2}
 DTYPE = {np.dtype(np.float16): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}
 # (lattice, collision code) pairs the library instantiates: base | 4 = forced (XLBN_COLLISION_FORCED), | 8 = lean KBC (kLeanKbc)
 PARTS = [("D3Q19", 0), ("D3Q19", 4), ("D3Q19", 2), ("D3Q19", 6), ("D3Q27", 0), ("D3Q27", 1), ("D3Q27", 4), ("D3Q27", 5), ("D3Q27", 2), ("D3Q27", 6),
-         ("D3Q27", 9), ("D2Q9", 0), ("D2Q9", 1), ("D2Q9", 4), ("D2Q9", 5), ("D2Q9", 9), ("D2Q9X", 0), ("D2Q9X", 1), ("D3Q27", 17), ("D2Q9", 17)]  # fmt: skip
+         ("D3Q27", 9), ("D2Q9", 0), ("D2Q9", 1), ("D2Q9", 4), ("D2Q9", 5), ("D2Q9", 9), ("D2Q9X", 0), ("D2Q9X", 1), ("D3Q27", 17), ("D2Q9", 17), ("D3Q27", 13), ("D2Q9", 13)]  # fmt: skip
 SYM = lambda lat, coll: f"mirror_step_{'0x' if lat == 'D2Q9X' else LATTICE[lat]}_{coll}"  # noqa: E731
 
 
@@ -175,6 +175,16 @@ def test_slab_decomposition_through_ghost_planes_is_bit_identical(mirror, name, 
 def test_lean_kbc_variant_matches_the_reference_vectors(mirror, name):
     """cells_per_thread = 301: the register-lean arrangement of the KBC collision (a tuning candidate for round 2) holds the
     same tolerance against the reference and stays within rounding of the default formulation."""
+    g = load_golden(name)
+    lean = mirror_run(mirror, g, lean_kbc=True)
+    assert rel_err(lean, g["f_final"]) <= RTOL[g["policy"]]
+    assert rel_err(lean, mirror_run(mirror, g)) <= 3e-6
+
+
+@pytest.mark.parametrize("name", [n for n in WARP_CASES_N4 if "kbc_forced" in n])
+def test_lean_kbc_under_forced_collision_matches_the_reference_vectors(mirror, name):
+    """ForcedCollision(KBC): the lean formulation with the ExactDifference term added in its last pass (what cells_per_thread = 0 selects)
+    against the reference's WARP-backend vector and against the literal arrangement."""
     g = load_golden(name)
     lean = mirror_run(mirror, g, lean_kbc=True)
     assert rel_err(lean, g["f_final"]) <= RTOL[g["policy"]]

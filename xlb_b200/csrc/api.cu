@@ -64,6 +64,8 @@ template <> int dispatch_step<D2Q9, XLBN_KBC | kExactKbc>(const StepCall&);
 template <> int dispatch_step<D2Q9X, XLBN_BGK>(const StepCall&);  // 2-D x-slab axis order (step_inst_d2q9x.cu)
 template <> int dispatch_step<D2Q9X, XLBN_KBC>(const StepCall&);
 template <> int dispatch_step<D2Q9X, XLBN_KBC | kLeanKbc>(const StepCall&);
+template <> int dispatch_step<D3Q27, XLBN_KBC | kLeanKbc | kF>(const StepCall&);
+template <> int dispatch_step<D2Q9, XLBN_KBC | kLeanKbc | kF>(const StepCall&);
 }  // namespace xlbn
 
 extern "C" {
@@ -275,9 +277,9 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
     c.out_hi = halo_ghost(halo, halo->peer_hi, p_out, 0);
     c.out_lo = halo_ghost(halo, halo->peer_lo, p_out, 1);
   }
-  if (s->cells_per_thread == 301 && s->forced) return fail(XLBN_E_UNSUPPORTED, "xlbn_step: the lean KBC variant (cells_per_thread = 301) has no forced form");
   // KBC: the register-lean formulation is the default (B200: 0.81 vs 0.69 of the HBM roofline, profiles/r2_*); 300 = literal
-  const bool lean = s->collision == XLBN_KBC && !s->forced && (s->cells_per_thread == 0 || s->cells_per_thread == 301);
+  // (forced KBC: the lean form too, except in the 2-D slab axis order, where the forced operators are not built)
+  const bool lean = s->collision == XLBN_KBC && (s->cells_per_thread == 0 || s->cells_per_thread == 301) && !(s->forced && slab_2d);
   const bool exact_kbc = s->collision == XLBN_KBC && !s->forced && s->cells_per_thread == 300 && !slab_2d;
   const int coll = s->collision | (s->forced ? kF : 0) | (lean ? kLeanKbc : 0) | (exact_kbc ? kExactKbc : 0);
   switch (s->lattice) {
@@ -296,6 +298,7 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
         case XLBN_BGK | kF: return dispatch_step<D3Q27, XLBN_BGK | kF>(c);
         case XLBN_KBC | kF: return dispatch_step<D3Q27, XLBN_KBC | kF>(c);
         case XLBN_KBC | kLeanKbc: return dispatch_step<D3Q27, XLBN_KBC | kLeanKbc>(c);
+        case XLBN_KBC | kLeanKbc | kF: return dispatch_step<D3Q27, XLBN_KBC | kLeanKbc | kF>(c);
         case XLBN_KBC | kExactKbc: return dispatch_step<D3Q27, XLBN_KBC | kExactKbc>(c);
         case XLBN_SMAGORINSKY_LES_BGK: return dispatch_step<D3Q27, XLBN_SMAGORINSKY_LES_BGK>(c);
         case XLBN_SMAGORINSKY_LES_BGK | kF: return dispatch_step<D3Q27, XLBN_SMAGORINSKY_LES_BGK | kF>(c);
@@ -316,6 +319,7 @@ int xlbn_step(xlbn_stepper* s, const void* f0, void* f1, const uint8_t* bc_mask,
         case XLBN_BGK | kF: return dispatch_step<D2Q9, XLBN_BGK | kF>(c);
         case XLBN_KBC | kF: return dispatch_step<D2Q9, XLBN_KBC | kF>(c);
         case XLBN_KBC | kLeanKbc: return dispatch_step<D2Q9, XLBN_KBC | kLeanKbc>(c);
+        case XLBN_KBC | kLeanKbc | kF: return dispatch_step<D2Q9, XLBN_KBC | kLeanKbc | kF>(c);
         case XLBN_KBC | kExactKbc: return dispatch_step<D2Q9, XLBN_KBC | kExactKbc>(c);
       }
       break;

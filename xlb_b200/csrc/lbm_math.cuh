@@ -272,8 +272,10 @@ __host__ __device__ constexpr bool kbc_has_shear() {
   else return l != 0;
 }
 
-template <class L, class TC, bool FAST>
-XLBN_DEV void collide_kbc_lean(TC (&f)[L::Q], TC omega) {
+// FORCED: ForcedCollision's ExactDifference term (exact_difference_force.py:79-84), + feq(rho, u + F) - feq(rho, u), is added in pass 3,
+// where feq_l(rho, u) is at hand anyway: one more feq_one per population instead of a second q-vector.
+template <class L, class TC, bool FAST, bool FORCED = false>
+XLBN_DEV void collide_kbc_lean(TC (&f)[L::Q], TC omega, const TC* force = nullptr) {
   static_assert(L::ID == XLBN_D3Q27 || L::ID == XLBN_D2Q9, "KBC: D3Q27 and D2Q9 only (kbc.py:71-72)");
   TC rho, u[L::D];
   macroscopic<L, TC, FAST>(f, rho, u);
@@ -331,10 +333,19 @@ XLBN_DEV void collide_kbc_lean(TC (&f)[L::Q], TC omega) {
   launder(usqr);
   XLBN_FOR(L::D, d) launder(u[d]); XLBN_END
   const TC bg = beta * gamma, b2 = beta * (TC(2.0) - gamma);
+  TC uf[L::D], usqr_f = TC(0);
+  if constexpr (FORCED) {
+    XLBN_FOR(L::D, d) uf[d] = u[d] + force[d]; XLBN_END
+    TC uuf = uf[0] * uf[0];
+    XLBN_FOR(L::D - 1, d) uuf = fma_(uf[d + 1], uf[d + 1], uuf); XLBN_END
+    usqr_f = TC(1.5) * uuf;
+  }
   XLBN_FOR(L::Q, l)
-    const TC fneq = f[l] - feq_one<L, TC, l>(rho, u, usqr);
+    const TC feq = feq_one<L, TC, l>(rho, u, usqr);
+    const TC fneq = f[l] - feq;
     TC out = fma_(-bg, fneq, f[l]);
     if constexpr (kbc_has_shear<L, l>()) out = fma_(-b2, kbc_ds<L, TC, l>(sv), out);
+    if constexpr (FORCED) out += feq_one<L, TC, l>(rho, uf, usqr_f) - feq;
     f[l] = out;
   XLBN_END
 }
@@ -344,8 +355,14 @@ XLBN_DEV void collide_kbc_lean(TC (&f)[L::Q], TC omega) {
 template <class L, int COLL, class TC, bool FAST = false>
 XLBN_DEV void collide_cell_ext(TC (&f)[L::Q], TC omega, const double* force, double smagorinsky) {
   if constexpr ((COLL & kLeanKbc) != 0) {
-    static_assert(kBaseCollision<COLL> == XLBN_KBC && !kForcedCollision<COLL>, "the lean formulation exists for plain KBC only");
-    collide_kbc_lean<L, TC, FAST>(f, omega);
+    static_assert(kBaseCollision<COLL> == XLBN_KBC, "the lean formulation exists for KBC only");
+    if constexpr (kForcedCollision<COLL>) {
+      TC fv[L::D];
+      XLBN_FOR(L::D, d) fv[d] = (TC)force[d]; XLBN_END
+      collide_kbc_lean<L, TC, FAST, true>(f, omega, fv);
+    } else {
+      collide_kbc_lean<L, TC, FAST>(f, omega);
+    }
     return;
   }
   TC rho, u[L::D], feq[L::Q], out[L::Q];

@@ -8,4 +8,7 @@ namespace xlbn {
 XLBN_DEFINE_STEP_DISPATCH(D3Q27, XLBN_KBC | kLeanKbc)
 XLBN_DEFINE_STEP_DISPATCH(D2Q9, XLBN_KBC | kLeanKbc)
 XLBN_DEFINE_STEP_DISPATCH(D2Q9X, XLBN_KBC | kLeanKbc)
+// ... and under ForcedCollision (ExactDifference added in the last pass)
+XLBN_DEFINE_STEP_DISPATCH(D3Q27, XLBN_KBC | kLeanKbc | XLBN_COLLISION_FORCED)
+XLBN_DEFINE_STEP_DISPATCH(D2Q9, XLBN_KBC | kLeanKbc | XLBN_COLLISION_FORCED)
 }  // namespace xlbn
