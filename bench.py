@@ -58,6 +58,71 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class NvmlClockSampler:
+    """SM clock and clock-event (throttle) reasons through NVML — what nvidia-smi itself reads — sampled every 5 ms by a thread of this
+    process, time-stamped, so that even a 60 ms timed region holds a dozen samples.  Preferred over the nvidia-smi child process below,
+    whose first line can arrive after a short region has ended (and whose buffered output is lost when it is terminated)."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def __init__(self, torch, device_index):
+        import threading
+
+        import pynvml
+
+        pynvml.nvmlInit()
+        self.nv = pynvml
+        handle = None
+        try:  # the CUDA ordinal is not the NVML index under CUDA_VISIBLE_DEVICES: go through the UUID
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            handle = None
+        self.handle = handle if handle is not None else pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        self.read_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.sample()  # fails here, not in the thread, if the queries are unsupported
+        self.rows, self.stop_flag = [], threading.Event()
+        self.thread = threading.Thread(target=self.loop, daemon=True)
+
+    def sample(self):
+        return (time.time(), float(self.nv.nvmlDeviceGetClockInfo(self.handle, self.nv.NVML_CLOCK_SM)), int(self.read_reasons(self.handle)))
+
+    def loop(self):
+        while not self.stop_flag.is_set():
+            try:
+                self.rows.append(self.sample())
+            except Exception:
+                pass
+            self.stop_flag.wait(0.005)
+
+    def start(self):
+        self.thread.start()
+
+    def stop(self, t_begin=None, t_end=None):
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        rows = list(self.rows)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+        inside = [r for r in rows if t_begin is not None and t_begin <= r[0] <= t_end]
+        window = "timed region"
+        if not inside:
+            inside, window = rows, "warm-up + timed region (no sample fell inside the region)"
+        bits = 0
+        for r in inside:
+            bits |= r[2]
+        return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": self.max_mhz, "reasons": [n for n, b in self.REASONS if bits & b],
+                "samples": len(inside), "window": window, "source": "NVML (pynvml), 5 ms period"}  # fmt: skip
+
+
+def clock_sampler(torch, device_index):
+    try:
+        return NvmlClockSampler(torch, device_index)
+    except Exception:
+        return ClockSampler(device_index)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Started before the warm-up (the
     process takes ~0.1 s to produce its first line, longer than a 20-step timed region at 512^3); samples are time-stamped and
@@ -238,7 +303,9 @@ def roofline_of(args, shape, world, ms_per_step):
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):  # ncu --set full captures, keyed by the complete workload (config, lattice, collision, policy, local extents)
         try:
-            key = f"{args.config}_{args.lattice}_{args.collision}_{args.policy}_{shape[0] // world}x{shape[1]}x{shape[2]}"
+            key = f"{args.config}_{args.lattice}_{args.collision}{'_forced' if getattr(args, 'force', 0.0) else ''}_{args.policy}_{shape[0] // world}x{shape[1]}x{shape[2]}"
+            if str(getattr(args, "cells_per_thread", 0)) not in ("0", "default"):
+                key += f"_v{args.cells_per_thread}"  # a capture belongs to the kernel the library picks by default
             entry = json.load(open(traffic_file)).get(key)
             if entry is not None:
                 out["traffic"] = entry["bytes"] if isinstance(entry, dict) else entry
@@ -299,7 +366,7 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
+    sampler = clock_sampler(torch, local_rank) if rank == 0 else None
     if rank == 0:
         sampler.start()
     ms, fields, window = timed_steps(torch, stepper, fields, omega, args.steps, warmup, barrier)

@@ -163,7 +163,7 @@ def c_oracle_run(g, steps=None):
     return f, bc_mask, missing
 
 
-def tile_case(lattice, shape, steps, seed, walls=True, policy="FP32FP16"):
+def tile_case(lattice, shape, steps, seed, walls=True, policy="FP32FP16", collision="BGK", force=None, smagorinsky=0.17):
     """A closed box (EquilibriumBC lid + FullwayBounceBack walls: mlups_3d.py:45-63) or a periodic box, from a seeded random state (FP32FP16 unless told otherwise)."""
     from oracle import lbm_numpy as O
 
@@ -171,7 +171,8 @@ def tile_case(lattice, shape, steps, seed, walls=True, policy="FP32FP16"):
     rng = np.random.default_rng(seed)
     f_init = O.initialize_eq(shape, lat, policy, rho=1 + 1e-2 * rng.standard_normal((1,) + shape), u=2e-2 * rng.standard_normal((3,) + shape))
     g = load_golden("cavity_d3q19_bgk_fp32fp16")
-    g.update(lattice=lattice, shape=shape, steps=steps, omega=1.6, policy=policy, collision="BGK", f_init=f_init, bcs=[], n_bc=0)
+    g.update(lattice=lattice, shape=shape, steps=steps, omega=1.6, policy=policy, collision=collision, f_init=f_init, bcs=[], n_bc=0,
+             force_vector=None if force is None else np.asarray(force, dtype=np.float64), smagorinsky=smagorinsky)
     if walls:
         box, box_ne = O.bounding_box_indices(shape), O.bounding_box_indices(shape, remove_edges=True)
         w = np.unique(np.concatenate([box[k] for k in ("bottom", "left", "right", "front", "back")], axis=1), axis=-1)

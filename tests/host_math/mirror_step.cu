@@ -163,7 +163,7 @@ int host_step_tile1(const StepCall& c) {
 
 template <class L, int COLL, class TC, class TS>
 int host_step_v(const StepCall& c) {
-  if constexpr (COLL == XLBN_BGK && sizeof(TS) == 4 && L::D == 3)
+  if constexpr ((COLL == XLBN_BGK || (kExtCollision<COLL> && (COLL & (kLeanKbc | kExactKbc)) == 0)) && sizeof(TS) == 4 && L::D == 3)
     if (c.requested_v == 501) return host_step_tile1<L, COLL, TC, TS>(c);
   if constexpr (COLL == XLBN_BGK && sizeof(TC) == 4 && sizeof(TS) == 2 && L::D == 3)
     if (c.requested_v == 404) return host_step_tile<L, 512>(c);

@@ -291,6 +291,18 @@ def test_scalar_tile_kernel_logic_is_bit_identical_to_the_reference_kernel(mirro
     assert np.array_equal(f, ref), f"{int((f != ref).sum())} of {f.size} values differ, rel err {rel_err(f, ref):.3e}"
 
 
+@pytest.mark.parametrize("collision,force", [("BGK", (1e-5, 0.0, -2e-5)), ("SmagorinskyLESBGK", None), ("SmagorinskyLESBGK", (1e-5, 0.0, -2e-5))])
+def test_scalar_tile_kernel_logic_with_the_extended_collision_operators(mirror, collision, force):
+    """The extended operators on D3Q19 FP32FP32 through the scalar tile kernel's per-thread code: same bits as the direct-load path."""
+    from common import c_oracle_run
+
+    g = tile_case("D3Q19", (3, 8, 64), 6, 19, True, "FP32FP32", collision, force)
+    ref, _, _ = c_oracle_run(g)
+    direct = mirror_run(mirror, g)
+    assert rel_err(direct, ref) <= RTOL["FP32FP32"]
+    assert np.array_equal(mirror_run(mirror, g, v=501), direct)
+
+
 def test_tile_kernel_logic_with_every_boundary_kind(mirror):
     """Regularized inlet, ExtrapolationOutflow outlet, Halfway body, 255 cells: the scalar boundary routine inside the tile path."""
     from common import c_oracle_run

@@ -160,6 +160,21 @@ def test_scalar_tile_kernel_is_bit_identical_to_the_reference_kernel(lattice, sh
         assert np.array_equal(f, ref), f"cells_per_thread={v}: {int((f != ref).sum())} of {f.size} values differ from the reference kernel's, rel err {rel_err(f, ref):.3e}"
 
 
+@pytest.mark.parametrize("collision,force", [("BGK", (1e-5, 0.0, -2e-5)), ("SmagorinskyLESBGK", None), ("SmagorinskyLESBGK", (1e-5, 0.0, -2e-5))])
+@pytest.mark.parametrize("shape,walls", [((3, 4, 512), True), ((40, 64, 64), True), ((2, 64, 16), False)])
+def test_scalar_tile_kernel_with_the_extended_collision_operators(collision, force, shape, walls):
+    """SmagorinskyLESBGK on D3Q19 FP32FP32 takes the scalar tile kernel by default where the slab can be tiled, the forced operators on
+    request (cells_per_thread 501): same bits as the direct-load kernel (same per-cell code), reference tolerance against the C
+    restatement of the reference kernel."""
+    g = tile_case("D3Q19", shape, 12, 19, walls, "FP32FP32", collision, force)
+    ref, _, _ = c_oracle_run(g)
+    direct, _, _ = native_run(g, cells_per_thread=1)
+    assert rel_err(direct, ref) <= RTOL["FP32FP32"]
+    for v in (0, 501):
+        f, _, _ = native_run(g, cells_per_thread=v)
+        assert np.array_equal(f, direct), f"cells_per_thread={v}: {int((f != direct).sum())} of {f.size} values differ from the direct-load kernel's"
+
+
 def test_scalar_tile_kernel_with_every_boundary_kind_and_solid_cells():
     from oracle import lbm_numpy as O
 

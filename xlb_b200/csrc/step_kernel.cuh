@@ -957,13 +957,30 @@ int launch_step_base(const StepParams<TS>& p, int x_count, int requested_v, cons
   }
 }
 
-// Extended collision models (SmagorinskyLESBGK, forced operators): the one-cell-per-thread scalar kernel only — the
-// layout that won every comparison for the base operators; cells_per_thread is ignored.
+// Extended collision models (SmagorinskyLESBGK, forced operators): one cell per thread — D3Q19 with fp32 storage can take the scalar
+// tile kernel where the slab can be tiled (cells_per_thread 501; 0 picks it for unforced SmagorinskyLESBGK), everything else the
+// direct-load kernel; other cells_per_thread values are ignored.
 template <class L, int COLL, class TC, class TS>
 int launch_step(const StepParams<TS>& p, int x_count, int requested_v, const void* f0, const void* f1, const void* g0, const void* g1,
                 const void* o0, const void* o1, BcEntry* table_rw, double* eq_omega_state, cudaStream_t stream) {
-  if constexpr (kExtCollision<COLL>) return launch_step_v<L, COLL, TC, TS, 1>(p, x_count, stream);
-  else return launch_step_base<L, COLL, TC, TS>(p, x_count, requested_v, f0, f1, g0, g1, o0, o1, table_rw, eq_omega_state, stream);
+  if constexpr (kExtCollision<COLL>) {
+#if !XLBN_ON_HOST
+    // D3Q19 with fp32 storage: the scalar tile kernel (step_tile.cuh) wherever the slab can be tiled, as for plain BGK
+    if constexpr (L::Q == 19 && L::D == 3 && sizeof(TS) == 4) {
+      const bool fits = tile1_eligible<L, TS>(p, f0, f1, g0, g1, o0 != nullptr || o1 != nullptr);
+      if (requested_v == 501 && !fits)
+        return fail(XLBN_E_SHAPE, "cells_per_thread = 501: the scalar tile kernel needs nz | 512, nz %% 16 == 0, ny %% (512 / nz) == 0, 16-byte aligned arrays and no halo handle (nz = %d, ny = %d)", p.nz, p.ny);
+      // By default for SmagorinskyLESBGK in fp32 (512^3 cavity: 1.02 of the measured copy bandwidth against 0.93 for the direct-load
+      // kernel); the forced operators only on request: the second equilibrium makes them issue-bound with the tile kernel's 16 warps
+      // (forced BGK 0.835 against 0.876, forced Smagorinsky 0.825 against 0.822; profiles/r2_call19_matrix.txt), and the fp64 forced
+      // Smagorinsky instantiation spills 330 bytes at 96 registers.
+      if ((requested_v == 501 || (requested_v == 0 && sizeof(TC) == 4 && !kForcedCollision<COLL>)) && fits) return launch_step_tile1<L, COLL, TC, TS, 1>(p, x_count, stream);
+    }
+#endif
+    return launch_step_v<L, COLL, TC, TS, 1>(p, x_count, stream);
+  } else {
+    return launch_step_base<L, COLL, TC, TS>(p, x_count, requested_v, f0, f1, g0, g1, o0, o1, table_rw, eq_omega_state, stream);
+  }
 }
 
 // One entry per (lattice, collision); dispatches on (compute, store) dtype.  Defined in step_inst_*.cu.
