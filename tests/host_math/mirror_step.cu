@@ -105,16 +105,11 @@ int host_step_tile(const StepCall& c) {
     const TileGeom g = tile_geom(p, tile, rows, tiles_per_plane);
     memset(in, 0xff, sizeof(in));
     for (int l = 0; l < L::Q; ++l) {  // the producer warp, lane l
-      const __half* src[2];
-      unsigned dst[2], count[2];
-      const int n = tile_plan<L>(p, l, L::ck(0, l), L::ck(1, l), g, rows, src, dst, count);
-      unsigned total = 0;
-      for (int i = 0; i < n; ++i) {
-        if ((reinterpret_cast<uintptr_t>(src[i]) % 16) || ((dst[i] * 2u) % 16) || ((count[i] * 2u) % 16)) return fail(XLBN_E_SHAPE, "mirror: bulk copy not 16-byte aligned");
-        memcpy(in + l * kTileRowBytes + dst[i] * 2u, src[i], count[i] * 2u);
-        total += count[i];
-      }
-      if (total != (unsigned)kTileCells) return fail(XLBN_E_SHAPE, "mirror: copy plan covers %u of 512 elements", total);
+      const TileRuns<__half> r = tile_runs<L, __half>(p, l, L::ck(0, l), L::ck(1, l), g, rows);
+      if (r.n0 + r.n1 != (unsigned)kTileCells) return fail(XLBN_E_SHAPE, "mirror: copy plan covers %u of %d elements", r.n0 + r.n1, kTileCells);
+      if ((reinterpret_cast<uintptr_t>(r.src0) % 16) || ((r.n0 * 2u) % 16) || (r.n1 && (reinterpret_cast<uintptr_t>(r.src1) % 16))) return fail(XLBN_E_SHAPE, "mirror: bulk copy not 16-byte aligned");
+      memcpy(in + l * kTileRowBytes, r.src0, r.n0 * 2u);
+      if (r.n1) memcpy(in + l * kTileRowBytes + r.n0 * 2u, r.src1, r.n1 * 2u);
     }
     memcpy(in + L::Q * kTileRowBytes, p.bc + g.cell0, kTileCells);
     for (unsigned t = 0; t < (unsigned)kTileConsumers; ++t) {  // the consumer threads

@@ -95,46 +95,11 @@ XLBN_DEVFN inline TileGeom tile_geom(const StepParams<TS>& p, int tile, int rows
   return g;
 }
 
-// Where population l of a tile comes from: up to two contiguous runs (elements), in the order they are laid out in the stage row.
+// Where population l of a tile comes from: up to two contiguous runs (elements), in the order they are laid out in the stage row: run 0 =
+// n0 elements from src0 to the start of the row, run 1 = n1 elements (0: none) from src1 right behind it.
 // (cx, cy) = kernel-axis velocity components of population l: the producer lane looks them up once, before its tile loop.
-template <class L, class TS>
-XLBN_DEVFN int tile_plan(const StepParams<TS>& p, int l, int cx, int cy, const TileGeom& g, int rows, const TS* (&src)[2], unsigned (&dst)[2], unsigned (&count)[2]) {
-  const int tab = (cx == 1 && g.x == 0) ? 1 : ((cx == -1 && g.x == p.nx - 1) ? 2 : 0);  // ghost plane / periodic wrap in x (fill_step_params)
-  const TS* base = p.pull[tab][l] + (unsigned)g.x * (unsigned)p.plane;
-  const unsigned nz = (unsigned)p.nz;
-  const int ys = g.y0 - cy;  // first source row: pull from y - c_y (stream.py:66-78)
-  if (ys < 0) {  // row ny-1, then rows 0 .. rows-2
-    src[0] = base + (unsigned)(p.ny - 1) * nz;
-    dst[0] = 0;
-    count[0] = nz;
-    if (rows == 1) return 1;
-    src[1] = base;
-    dst[1] = nz;
-    count[1] = (unsigned)(rows - 1) * nz;
-    return 2;
-  }
-  if (ys + rows > p.ny) {  // rows ys .. ny-1, then row 0
-    int n = 0;
-    if (rows > 1) {
-      src[n] = base + (unsigned)ys * nz;
-      dst[n] = 0;
-      count[n] = (unsigned)(rows - 1) * nz;
-      ++n;
-    }
-    src[n] = base;
-    dst[n] = (unsigned)(rows - 1) * nz;
-    count[n] = nz;
-    return n + 1;
-  }
-  src[0] = base + (unsigned)ys * nz;
-  dst[0] = 0;
-  count[0] = (unsigned)rows * nz;
-  return 1;
-}
-
-// The same plan as scalars (no local arrays, no run-time indexing): run 0 = n0 elements from src0 to the start of the stage row, run 1 =
-// n1 elements (0: none) from src1 right behind it.  The scalar tile kernel uses this form: ptxas 12.9 merged dst[] and count[] of
-// tile_plan in that kernel's D3Q19 instantiation (wrong destination offsets on the wrapped rows; caught by the bit-identity tests).
+// Scalars on purpose.  The first version filled src[2] / dst[2] / count[2] arrays by run-time index, and ptxas 12.9 merged dst[] and count[]
+// in the scalar tile kernel's D3Q19 instantiation (wrong destination offsets on the wrapped rows; caught by the bit-identity tests).
 template <class TS>
 struct TileRuns {
   const TS *src0, *src1;
@@ -405,10 +370,10 @@ __global__ void __launch_bounds__(TileDims<CELLS>::kThreads, CTAS) step_tile_ker
       }
       __syncwarp();
       if (lane < L::Q) {
-        const __half* src[2];
-        unsigned dst[2], count[2];
-        const int n = tile_plan<L, __half>(p, lane, pcx, pcy, g, rows, src, dst, count);
-        for (int i = 0; i < n; ++i) bulk_load(stage + lane * kTileRowBytes + dst[i] * 2u, src[i], count[i] * 2u, full + s);
+        const TileRuns<__half> r = tile_runs<L, __half>(p, lane, pcx, pcy, g, rows);
+        unsigned char* row = stage + lane * kTileRowBytes;
+        bulk_load(row, r.src0, r.n0 * 2u, full + s);
+        if (r.n1) bulk_load(row + r.n0 * 2u, r.src1, r.n1 * 2u, full + s);
       } else if (lane == L::Q) {
         bulk_load(stage + L::Q * kTileRowBytes, p.bc + g.cell0, kTileCells, full + s);
       }
