@@ -289,6 +289,21 @@ def config_dict(args, world, shape, omega):
     }  # fmt: skip
 
 
+def kernel_label(args, shape):
+    """Name of the kernel the library picks for this workload (csrc/step_kernel.cuh: launch_step / launch_step_base), for the roofline
+    object; an ncu capture of the same workload (profiles/traffic.json) overrides it with the name the profiler saw."""
+    ny, nz = shape[1], shape[2]
+    tiles = lambda cells, mult: nz <= cells and cells % nz == 0 and nz % mult == 0 and ny % (cells // nz) == 0  # noqa: E731
+    v = int(getattr(args, "cells_per_thread", 0) or 0)
+    forced = bool(getattr(args, "force", 0.0))
+    if args.policy == "FP32FP16" and args.collision == "BGK" and not forced and v in (0, 402, 404) and (tiles(1024, 8) or tiles(512, 8)):
+        return "xlbn::step_tile_kernel (TMA-fed, half2 pairs)"
+    if args.lattice == "D3Q19" and args.policy in ("FP32FP32", "FP64FP32") and tiles(512, 16) and v in (0, 501, 502):
+        if args.collision == "BGK" and not forced or v == 501 or (args.collision == "SmagorinskyLESBGK" and not forced and args.policy == "FP32FP32"):
+            return "xlbn::step_tile1_kernel (TMA-fed, one cell per thread)"
+    return "xlbn::step_kernel (direct loads)"
+
+
 def roofline_of(args, shape, world, ms_per_step):
     """Roofline of the dominant kernel: ONE fused-step launch per step covers the slab (the interior launch on slab grids)."""
     bytes_per_cell = 2 * Q[args.lattice] * STORE_BYTES[args.policy] + 1
@@ -298,7 +313,7 @@ def roofline_of(args, shape, world, ms_per_step):
     out = {
         "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
         "traffic": None, "bytes_per_cell": bytes_per_cell, "bytes_per_launch": bytes_per_cell * cells_local, "peak_source": peak_src,
-        "kernel": "xlbn::step_kernel", "launch_ms": round(ms_per_step, 4),
+        "kernel": kernel_label(args, (shape[0] // world, shape[1], shape[2])), "launch_ms": round(ms_per_step, 4),
     }  # fmt: skip
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):  # ncu --set full captures, keyed by the complete workload (config, lattice, collision, policy, local extents)
