@@ -303,6 +303,14 @@ def test_scalar_tile_kernel_logic_with_the_extended_collision_operators(mirror, 
     assert np.array_equal(mirror_run(mirror, g, v=501), direct)
 
 
+def test_scalar_tile_kernel_eligibility_rule(mirror):
+    """tile1_eligible (shared by the library's dispatch and the host mirror): nz | 512, nz % 16 == 0, ny a whole number of tiles."""
+    for shape in ((4, 16, 16), (2, 24, 32), (2, 64, 8)):  # 32-row tile in a 16-row plane; ny % 16 != 0; nz % 16 != 0
+        g = tile_case("D3Q19", shape, 1, 3, False, "FP32FP32")
+        with pytest.raises(AssertionError, match="not eligible"):
+            mirror_run(mirror, g, v=501)
+
+
 def test_tile_kernel_logic_with_every_boundary_kind(mirror):
     """Regularized inlet, ExtrapolationOutflow outlet, Halfway body, 255 cells: the scalar boundary routine inside the tile path."""
     from common import c_oracle_run

@@ -35,6 +35,51 @@ def test_reference_arm_prints_contract_line():
     assert line["e2e"] == {"value": line["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def _bench_module():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_bench_names_the_kernel_the_library_picks():
+    """roofline.kernel mirrors the dispatch rules of csrc/step_kernel.cuh (launch_step / launch_step_base)."""
+    import argparse
+
+    b = _bench_module()
+
+    def label(shape=(512, 512, 512), **kw):
+        return b.kernel_label(argparse.Namespace(**{**dict(lattice="D3Q19", collision="BGK", policy="FP32FP32", force=0.0, cells_per_thread=0), **kw}), shape)
+
+    assert "step_tile1_kernel" in label()
+    assert "step_tile1_kernel" in label(policy="FP64FP32")
+    assert "step_tile1_kernel" in label(collision="SmagorinskyLESBGK")
+    assert "step_kernel (direct" in label(force=1e-5)  # forced operators: on request only
+    assert "step_tile1_kernel" in label(force=1e-5, cells_per_thread=501)
+    assert "step_kernel (direct" in label(cells_per_thread=1)
+    assert "step_kernel (direct" in label(lattice="D3Q27")
+    assert "step_kernel (direct" in label(lattice="D3Q27", collision="KBC")
+    assert "step_tile_kernel" in label(policy="FP32FP16") and "step_tile_kernel" in label(policy="FP32FP16", lattice="D3Q27")
+    assert "step_kernel (direct" in label(shape=(16, 16, 16))  # a 512-cell tile would be 32 rows of a 16-row plane
+    assert "step_kernel (direct" in label(shape=(64, 24, 32))  # ny is not a whole number of tiles
+
+
+def test_clock_sampler_falls_back_without_nvml():
+    """No GPU here: NVML cannot initialise, bench.py must fall back to the nvidia-smi sampler and still return a clocks object."""
+    import torch
+
+    b = _bench_module()
+    s = b.clock_sampler(torch, 0)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the NVML sampler is used")
+    assert type(s).__name__ == "ClockSampler"
+    s.start()
+    out = s.stop(0.0, 1.0)
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     proc = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"], cwd=ROOT, capture_output=True, text=True, timeout=120, env=env)
