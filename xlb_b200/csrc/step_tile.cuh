@@ -1,7 +1,13 @@
-// The tile kernel: the fused step as a PERSISTENT, TMA-FED pipeline (FP32FP16 storage, BGK).  Same per-cell algebra, same results —
-// bit for bit — as step_kernel's half2-state path; what changes is how the bytes move.
+// The tile kernels: the fused step as a PERSISTENT, TMA-FED pipeline.  Same per-cell algebra, same results — bit for bit — as the
+// direct-load kernels of step_kernel.cuh; what changes is how the bytes move.  Two kernels share the pipeline (producer warp, copy plan
+// `tile_runs`, stage ring, mbarriers, direct stores):
+//   step_tile_kernel<L, CELLS, CTAS>           FP32FP16 storage, BGK: two z-neighbours per thread as half2 words, packed fp32x2 arithmetic
+//                                              (described first, below)
+//   step_tile1_kernel<L, COLL, TC, TS, CTAS>   any storage type / collision, one cell per thread around the per-cell code of the direct
+//                                              kernel; the default for D3Q19 BGK with fp32 storage — the headline path (second half of
+//                                              this file)
 //
-// Why.  With fp16 storage the step moves 77 B per cell and needs ~230 instructions per cell: the direct-load kernel keeps at most
+// Why (written for the fp16 kernel, which came first).  With fp16 storage the step moves 77 B per cell and needs ~230 instructions per cell: the direct-load kernel keeps at most
 // 32 warps/SM resident (64 registers, two cells per thread), every one of them parked on its own 29 loads (ncu: long_scoreboard 62 %,
 // one eligible warp per cycle, 26 of 64 warp slots) — it stops at 0.71 (cavity) / 0.84 (periodic) of the HBM roofline, and 40 % of
 // its integer work is 64-bit address arithmetic for 48 global accesses per thread.  Memory-level parallelism is tied to registers.
