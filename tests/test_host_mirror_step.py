@@ -348,6 +348,14 @@ def test_tile_kernel_logic_with_every_boundary_kind(mirror):
         for v in (402, 404):  # 1024- and 512-cell tiles
             f = mirror_run(mirror, g, v=v)
             assert np.array_equal(f, ref), f"{name} v={v}: {int((f != ref).sum())} of {f.size} values differ, rel err {rel_err(f, ref):.3e}"
+        # the same set-up with fp32 storage through the scalar tile kernel's per-thread code (cells_per_thread 501)
+        for policy in ("FP32FP32", "FP64FP32"):
+            g1 = dict(g)
+            g1.update(policy=policy, f_init=O.initialize_eq(shape, lat, policy))
+            g1["bcs"] = [dict(b, prescribed=np.asarray(b["prescribed"], dtype=np.float32)) if "prescribed" in b and np.ndim(b["prescribed"]) > 0 else b for b in bcs]
+            ref1, _, _ = c_oracle_run(g1)
+            f1 = mirror_run(mirror, g1, v=501)
+            assert np.array_equal(f1, ref1), f"{name} {policy} v=501: {int((f1 != ref1).sum())} of {f1.size} values differ, rel err {rel_err(f1, ref1):.3e}"
 
 
 @pytest.mark.parametrize("name", ["cavity_d2q9_bgk_fp32", "cavity_d2q9_kbc_fp32", "channel2d_d2q9_bgk_outflow_fp32", "channel2d_d2q9_bgk_zouhe_pressure_fp32", "warp_channel2d_d2q9_bgk_regpressure"])
